@@ -1,0 +1,287 @@
+"""Device-resident Stein problem: host-side orchestration above the C ABI.
+
+PyTorch is used only to own device buffers and streams; every arithmetic step of the path
+(standardisation, median heuristic, log-weights, pair kernels, greedy search, KSD sums)
+is a libgfk call.  Nothing here falls back to the CPU.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Problem, check
+
+WEIGHT_SCALE_THRESHOLD = 10     # stein_thinning.thinning.WEIGHT_SCALE_THRESHOLD
+MEDIAN_SUBSAMPLE = 1000         # rows entering the median heuristic
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError('gradient_free_mcmc_postprocessing_b200 needs a CUDA device (sm_100a); '
+                           'there is no CPU fallback')
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise ValueError(f'device must be a CUDA device, got {device}')
+    if device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    return device
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _to_device_f64(a, device, name):
+    """numpy array / CPU tensor (pinned or not) / CUDA tensor -> contiguous float64 CUDA tensor."""
+    if isinstance(a, torch.Tensor):
+        t = a
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        if t.device != device:
+            t = t.to(device, non_blocking=True)
+        return t.contiguous()
+    arr = np.ascontiguousarray(np.asarray(a), dtype=np.float64)
+    if arr.size == 0:
+        return torch.empty(arr.shape, dtype=torch.float64, device=device)
+    return torch.from_numpy(arr).to(device, non_blocking=False)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _bytes(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def scalar_linv(value, d):
+    """``inv(value * I)`` exactly as ``stein_thinning.kernel.make_precon`` forms it."""
+    return np.linalg.inv(value * np.identity(d))
+
+
+def median_sq_device(x_dev, device):
+    """Squared median pairwise distance of the (<= 1000-row subsample of the) device sample."""
+    lib = _lib.load()
+    n, d = x_dev.shape
+    if n < 2:
+        raise Exception('Too few unique samples in sample.')
+    ws = _bytes(lib.gfk_median_ws_bytes(n, MEDIAN_SUBSAMPLE), device)
+    mid = (ctypes.c_double * 2)()
+    check(lib.gfk_median_pdist(_ptr(x_dev), n, d, MEDIAN_SUBSAMPLE, mid, _ptr(ws), _stream_ptr(device)))
+    # np.median of an even count is np.mean of the two middle order statistics
+    med = np.mean(np.array([mid[0], mid[1]]))
+    return med ** 2
+
+
+class SteinProblem:
+    """Standardised sample, scores, optional GF log-weights and preconditioner, resident in HBM.
+
+    Mirrors what ``_make_stein_integrand`` / ``_make_stein_gf_integrand`` capture in their
+    closures (reference: code/notebooks/examples/JAX_Stein_Thinning.ipynb#c16-#c17,
+    code/src/utils/ksd.py:25).
+    """
+
+    def __init__(self, sample, gradient, log_p=None, log_q=None, standardize=True, preconditioner='id',
+                 range_cap=None, precision=None, device=None, c=1.0):
+        lib = _lib.load()
+        self.c = float(c)
+        self.device = device = _require_cuda(device)
+        self.mode = _lib.mode_code(precision)
+        shape = tuple(sample.shape)
+        if len(shape) != 2:
+            raise ValueError('sample is not two-dimensional.')
+        n, d = shape
+        if n == 0 or d == 0:
+            raise ValueError('sample is empty.')
+        if tuple(gradient.shape) != (n, d):
+            raise ValueError('Dimensions of sample and gradient are inconsistent.')
+        if n >= 2 ** 32 - 1:
+            raise ValueError('n must be below 2**32 - 1 (uint32 indices).')
+        self.gf = log_p is not None
+        if self.gf and (tuple(np.shape(log_p)) != (n,) or tuple(np.shape(log_q)) != (n,)):
+            raise ValueError('Dimensions of sample and log-densities are inconsistent.')
+        self.n, self.d = n, d
+
+        with torch.cuda.device(device):
+            x_raw = _to_device_f64(sample, device, 'sample')
+            g_raw = _to_device_f64(gradient, device, 'gradient')
+            st = _stream_ptr(device)
+            # a3: validation + standardisation
+            self.x = torch.empty_like(x_raw)
+            self.s = torch.empty_like(g_raw)
+            ws = _bytes(lib.gfk_standardize_ws_bytes(n, d), device)
+            scl = (ctypes.c_double * d)()
+            rc = lib.gfk_standardize(_ptr(x_raw), _ptr(g_raw), n, d, int(bool(standardize)), _ptr(self.x),
+                                     _ptr(self.s), scl, _ptr(ws), st)
+            if rc == _lib.GFK_ENUMERIC:
+                raise ValueError(lib.gfk_last_error().decode())
+            check(rc)
+            self.scale = np.array(scl[:])
+            # a2: preconditioner
+            self.xl = None
+            self._set_preconditioner(preconditioner)
+            # a4: gradient-free log-weights
+            self.lw = self.w = None
+            if self.gf:
+                lp = _to_device_f64(log_p, device, 'log_p')
+                lq = _to_device_f64(log_q, device, 'log_q')
+                self.lw = torch.empty(n, dtype=torch.float64, device=device)
+                spread = ctypes.c_double(0.0)
+                lws = _bytes(lib.gfk_log_weights_ws_bytes(), device)
+                rc = lib.gfk_log_weights(_ptr(lp), _ptr(lq), n, int(range_cap is not None),
+                                         float(range_cap if range_cap is not None else 0.0), _ptr(self.lw),
+                                         ctypes.byref(spread), _ptr(lws), st)
+                if rc == _lib.GFK_ENUMERIC:
+                    raise ValueError(lib.gfk_last_error().decode())
+                check(rc)
+                if spread.value > WEIGHT_SCALE_THRESHOLD:
+                    warnings.warn(f'log_q differs from log_p by more than {WEIGHT_SCALE_THRESHOLD} - '
+                                  'consider using q that matches target better')
+            self._finalise_dtype()
+
+    # -- preconditioner -------------------------------------------------------------------------
+    def _set_preconditioner(self, preconditioner):
+        d, n = self.d, self.n
+        self.preconditioner = preconditioner
+        dense = None
+        if isinstance(preconditioner, np.ndarray):      # explicit linv (vfk0_imq)
+            linv = np.atleast_2d(np.asarray(preconditioner, dtype=float))
+            if linv.shape != (d, d):
+                raise ValueError('linv must be d x d')
+            if not np.array_equal(linv, linv[0, 0] * np.identity(d)):
+                dense = linv
+        elif preconditioner == 'id':
+            linv = np.identity(d)
+        elif preconditioner in ('med', 'sclmed'):
+            m2 = median_sq_device(self.x, self.device)
+            if m2 == 0:
+                raise Exception('Too few unique samples in sample.')
+            if preconditioner == 'sclmed':
+                m2 = m2 / np.log(np.minimum(MEDIAN_SUBSAMPLE, n))
+            linv = scalar_linv(m2, d)
+        elif preconditioner == 'smpcov':
+            cov = np.atleast_2d(torch.cov(self.x.T).cpu().numpy())
+            if not np.all(np.linalg.eigvals(cov) > 0):
+                raise Exception('Too few unique samples in sample.')
+            linv = dense = np.linalg.inv(cov)
+        else:
+            try:
+                value = float(preconditioner)
+            except (TypeError, ValueError):
+                raise ValueError('Incorrect preconditioner type.') from None
+            linv = scalar_linv(value, d)
+        self.linv = linv
+        if dense is None:
+            self.lam = float(linv[0, 0])
+            self.lam_sq = float(np.dot(linv, linv)[0, 0])
+        else:
+            # dense symmetric L: the kernels use xl = x @ L and unit lambda (stein_math.cuh)
+            sym = 0.5 * (dense + dense.T)
+            self.xl = self.x @ torch.from_numpy(sym).to(self.device)
+            self.lam = self.lam_sq = 1.0
+            if self.mode == _lib.F64_STRICT:
+                self.mode = _lib.F64_FAST   # numpy's BLAS summation order is not reproducible
+        self.trace = float(np.trace(linv))
+
+    def _finalise_dtype(self):
+        """Build the arrays the kernels read: float32 copies for f32, exp(lw) for the fast modes."""
+        lib = _lib.load()
+        st = _stream_ptr(self.device)
+        kx, ks, klw, kxl = self.x, self.s, self.lw, self.xl
+        if self.mode == _lib.F32_FAST:
+            def f32(t):
+                if t is None:
+                    return None
+                out = torch.empty(t.shape, dtype=torch.float32, device=self.device)
+                check(lib.gfk_to_f32(_ptr(t), _ptr(out), t.numel(), st))
+                return out
+            kx, ks, klw, kxl = f32(self.x), f32(self.s), f32(self.lw), f32(self.xl)
+        if self.gf and self.mode != _lib.F64_STRICT:
+            self.w = torch.empty_like(klw)
+            check(lib.gfk_exp_weights(_ptr(klw), _ptr(self.w), self.n, int(self.mode == _lib.F32_FAST), st))
+        self._kx, self._ks, self._klw, self._kxl = kx, ks, klw, kxl
+        self.struct = Problem(x=kx.data_ptr(), s=ks.data_ptr(),
+                              lw=klw.data_ptr() if klw is not None else None,
+                              w=self.w.data_ptr() if self.w is not None else None,
+                              xl=kxl.data_ptr() if kxl is not None else None,
+                              n=self.n, d=self.d, mode=self.mode, lambda_=self.lam, lambda_sq=self.lam_sq,
+                              trace=self.trace, c=self.c)
+
+    # -- operations -------------------------------------------------------------------------------
+    def thin(self, n_points, row_range=None, return_objective=False):
+        """``_greedy_search`` over this problem; returns ``np.ndarray`` of ``uint32`` (length n_points)."""
+        lib = _lib.load()
+        m = int(n_points)
+        if m < 1:
+            raise ValueError('n_points must be at least 1.')
+        if row_range is None:
+            from .distributed import shard_bounds
+            row_range = shard_bounds(self.n, lib.gfk_comm_size(), lib.gfk_comm_rank())
+        r0, r1 = row_range
+        with torch.cuda.device(self.device):
+            objective = torch.empty(r1 - r0, dtype=torch.float64, device=self.device)
+            idx = torch.empty(m, dtype=torch.int32, device=self.device)
+            ws = _bytes(lib.gfk_thin_ws_bytes(), self.device)
+            check(lib.gfk_thin(ctypes.byref(self.struct), r0, r1, m, _ptr(objective), _ptr(idx), _ptr(ws),
+                               _stream_ptr(self.device)))
+            out = idx.cpu().numpy().view(np.uint32)
+        if return_objective:
+            return out, objective
+        return out
+
+    def _sel(self, sel):
+        if sel is None:
+            return None
+        sel = np.ascontiguousarray(np.asarray(sel).astype(np.int64))
+        if sel.ndim != 1 or (sel.size and (sel.min() < 0 or sel.max() >= self.n)):
+            raise IndexError('selection indices out of range')
+        return torch.from_numpy(sel.astype(np.uint32).view(np.int32)).to(self.device)
+
+    def ksd(self, sel=None, m=None):
+        """Cumulative KSD over rows ``sel`` (or the first ``m`` rows); float64 ndarray of length m."""
+        lib = _lib.load()
+        sel_dev = self._sel(sel)
+        m = int(m if m is not None else (len(sel) if sel is not None else self.n))
+        with torch.cuda.device(self.device):
+            st = _stream_ptr(self.device)
+            low = torch.empty(m, dtype=torch.float64, device=self.device)
+            diag = torch.empty(m, dtype=torch.float64, device=self.device)
+            ks = torch.empty(m, dtype=torch.float64, device=self.device)
+            check(lib.gfk_ksd_rowsums(ctypes.byref(self.struct), _ptr(sel_dev), m, lib.gfk_comm_rank(),
+                                      lib.gfk_comm_size(), _ptr(low), _ptr(diag), st))
+            if lib.gfk_comm_size() > 1:
+                check(lib.gfk_allreduce_sum(_ptr(low), m, st))
+                check(lib.gfk_allreduce_sum(_ptr(diag), m, st))
+            check(lib.gfk_ksd_finish(_ptr(low), _ptr(diag), m, _ptr(ks), st))
+            return ks.cpu().numpy()
+
+    def kmat(self, sel=None, m=None):
+        lib = _lib.load()
+        sel_dev = self._sel(sel)
+        m = int(m if m is not None else (len(sel) if sel is not None else self.n))
+        with torch.cuda.device(self.device):
+            out = torch.empty((m, m), dtype=torch.float64, device=self.device)
+            check(lib.gfk_kmat(ctypes.byref(self.struct), _ptr(sel_dev), m, _ptr(out), _stream_ptr(self.device)))
+            return out.cpu().numpy()
+
+    def pairs(self, ia, ib):
+        """Element-wise ``k(ia[t], ib[t])`` (the integrand protocol); float64 ndarray."""
+        lib = _lib.load()
+        ia = np.ascontiguousarray(ia, dtype=np.int64)
+        ib = np.ascontiguousarray(ib, dtype=np.int64)
+        if ia.shape != ib.shape:
+            raise ValueError('index arrays must have the same shape')
+        for a in (ia, ib):
+            if a.size and (a.min() < 0 or a.max() >= self.n):
+                raise IndexError('index out of range')
+        with torch.cuda.device(self.device):
+            a_dev = torch.from_numpy(ia.reshape(-1)).to(self.device)
+            b_dev = torch.from_numpy(ib.reshape(-1)).to(self.device)
+            out = torch.empty(ia.size, dtype=torch.float64, device=self.device)
+            check(lib.gfk_pairs(ctypes.byref(self.struct), _ptr(a_dev), _ptr(b_dev), ia.size, _ptr(out),
+                                _stream_ptr(self.device)))
+            return out.cpu().numpy().reshape(ia.shape)

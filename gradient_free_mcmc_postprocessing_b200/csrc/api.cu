@@ -1,0 +1,115 @@
+// api.cu - error plumbing, device queries and the measurement helpers of libgfk.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gfk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return GFK_ECUDA;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// register-resident FMA chains: 8 independent accumulators per thread, 4096 x 8 x 2 FMAs each
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T seed) {
+    T a0 = seed + threadIdx.x, a1 = a0 + T(1), a2 = a0 + T(2), a3 = a0 + T(3);
+    T a4 = a0 + T(4), a5 = a0 + T(5), a6 = a0 + T(6), a7 = a0 + T(7);
+    const T m = T(0.9999999), c = T(1e-7);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            a0 = fma_t(a0, m, c); a1 = fma_t(a1, m, c); a2 = fma_t(a2, m, c); a3 = fma_t(a3, m, c);
+            a4 = fma_t(a4, m, c); a5 = fma_t(a5, m, c); a6 = fma_t(a6, m, c); a7 = fma_t(a7, m, c);
+        }
+    }
+    const T r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == T(-1)) out[0] = r;  // never true; keeps the chain alive
+}
+
+__global__ void flush_kernel(uint4* p, size_t count) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x)
+        p[e] = make_uint4((unsigned)e, 0u, 0u, 0u);
+}
+
+}  // namespace gfk
+
+using namespace gfk;
+
+extern "C" int gfk_version(void) { return GFK_VERSION; }
+extern "C" const char* gfk_last_error(void) { return g_err; }
+
+extern "C" int gfk_device_info(int* cc, int* sms, char* name, int name_len) {
+    int dev = 0;
+    GFK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    GFK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (cc) *cc = prop.major * 10 + prop.minor;
+    if (sms) *sms = prop.multiProcessorCount;
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return GFK_OK;
+}
+
+extern "C" int gfk_fma_peak(int is_f32, double* tflops_host, void* stream) {
+    GFK_REQUIRE(tflops_host, "gfk_fma_peak: NULL output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void* out = nullptr;
+    GFK_CUDA(cudaMalloc(&out, 64));
+    cudaEvent_t e0, e1;
+    GFK_CUDA(cudaEventCreate(&e0));
+    GFK_CUDA(cudaEventCreate(&e1));
+    const int iters = is_f32 ? 16384 : 8192;
+    const int grid = sm_count() * 8, threads = 256;
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        GFK_CUDA(cudaEventRecord(e0, st));
+        if (is_f32) fma_peak_kernel<float><<<grid, threads, 0, st>>>(static_cast<float*>(out), iters, 1.0f);
+        else fma_peak_kernel<double><<<grid, threads, 0, st>>>(static_cast<double*>(out), iters, 1.0);
+        GFK_CUDA(cudaEventRecord(e1, st));
+        GFK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        GFK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    const double flops = 2.0 * 16.0 * (double)iters * (double)grid * threads;
+    *tflops_host = flops / (best_ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" int gfk_flush_l2(void* scratch, size_t bytes, void* stream) {
+    GFK_REQUIRE(scratch && bytes >= 16, "gfk_flush_l2: bad arguments");
+    flush_kernel<<<sm_count() * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(scratch),
+                                                                               bytes / 16);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}

@@ -1,0 +1,414 @@
+// ksd.cu - O(m^2) kernel Stein discrepancy: tiled pair sums, cumulative KSD, Gram matrix.
+//
+// Replaces stein_thinning.stein.ksd / kmat (call sites code/src/utils/ksd.py:27,
+// code/tests/test_ksd.py:20; definition report/report.tex:309-313):
+//   ks[t] = sqrt( sum_{a,b<=t} k(a,b) ) / (t+1),   row t adds 2 sum_{b<t} k(t,b) + k(t,t).
+//
+// gfk_ksd_rowsums: one CTA per 64-row tile I walks the column tiles J <= I.  Row and column tiles
+// are staged in shared memory transposed ([k][row], conflict-free), in chunks of KC dimensions so any
+// d fits; each thread owns a 4 x 4 block of pairs and keeps the three running dot products
+// (<r,r>, <ds,r>, <sx,sy>) of every pair in registers - a GEMM-shaped loop on the FP64 (or FP32)
+// FMA pipe with ~0 bytes of HBM traffic per pair.  Row sums are reduced in a fixed order (no
+// atomics), so results are run-to-run reproducible and independent of the GPU count.
+#include "common.cuh"
+
+namespace gfk {
+
+constexpr int TILE = 64;     // rows / columns per tile
+constexpr int LD = TILE + 2; // padded leading dimension of a staged tile: keeps 16-byte alignment per k
+constexpr int MT = 4;        // micro-tile edge (pairs per thread = MT * MT)
+constexpr int KSD_THREADS = (TILE / MT) * (TILE / MT);  // 256
+
+template <typename T>
+struct KsdArgs {
+    const T* x;
+    const T* s;
+    const T* lw;
+    const T* w;
+    const T* xl;
+    const uint32_t* sel;
+    long long m;
+    KParams kp;
+    int part, n_parts;
+    double* low;
+    double* diag;
+};
+
+template <typename T>
+struct GView {
+    const T* p;
+    __device__ __forceinline__ T operator[](int k) const { return p[k]; }
+};
+
+template <typename T>
+__device__ __forceinline__ long long row_of(const KsdArgs<T>& a, long long t) {
+    return a.sel ? (long long)a.sel[t] : t;
+}
+
+// stage dimensions [k0, k0 + kc) of rows [t0, t0 + TILE) into dst[k][LD] (zero padded).
+// Consecutive threads read consecutive k of one row (coalesced); the padded LD spreads the stores.
+template <typename T, int KC>
+__device__ __forceinline__ void stage_tile(const KsdArgs<T>& a, const T* __restrict__ src, long long t0, int k0,
+                                           int kc, T* __restrict__ dst) {
+    const int d = a.kp.d;
+    for (int e = threadIdx.x; e < TILE * KC; e += KSD_THREADS) {
+        const int r = e / KC, k = e - r * KC;
+        const long long t = t0 + r;
+        T v = T(0);
+        if (k < kc && t < a.m) v = __ldg(src + row_of(a, t) * d + k0 + k);
+        dst[k * LD + r] = v;
+    }
+}
+
+// dynamic shared memory: xr sr xc sc [xlr xlc] each KC x LD, then wr[TILE] wc[TILE]
+template <typename T, bool DENSE, int KC>
+__global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char ksd_smem[];
+    T* xr = reinterpret_cast<T*>(ksd_smem);
+    T* sr = xr + KC * LD;
+    T* xc = sr + KC * LD;
+    T* sc = xc + KC * LD;
+    T* xlr = sc + KC * LD;
+    T* xlc = xlr + (DENSE ? KC * LD : 0);
+    T* wr = xlc + (DENSE ? KC * LD : 0);
+    T* wc = wr + TILE;
+
+    const long long ntiles = (a.m + TILE - 1) / TILE;
+    // this rank's tiles, largest (most column tiles) first
+    const long long my_tiles = (ntiles - a.part + a.n_parts - 1) / a.n_parts;
+    if ((long long)blockIdx.x >= my_tiles) return;
+    const long long I = a.part + (my_tiles - 1 - blockIdx.x) * (long long)a.n_parts;
+    const long long t0 = I * TILE;
+    const int ty = threadIdx.x / (TILE / MT), tx = threadIdx.x % (TILE / MT);
+    const int d = a.kp.d;
+    const bool gf = (a.lw != nullptr);
+    const bool pre_w = (a.w != nullptr);
+    const bool single_chunk = (d <= KC);
+
+    if (threadIdx.x < TILE) {
+        const long long t = t0 + threadIdx.x;
+        T v = T(0);
+        if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
+        wr[threadIdx.x] = v;
+    }
+    if (single_chunk) {   // the row tile is invariant over J: stage it once
+        stage_tile<T, KC>(a, a.x, t0, 0, d, xr);
+        stage_tile<T, KC>(a, a.s, t0, 0, d, sr);
+        if (DENSE) stage_tile<T, KC>(a, a.xl, t0, 0, d, xlr);
+    }
+    double rowacc[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) rowacc[i] = 0.0;
+
+    for (long long J = 0; J <= I; ++J) {
+        const long long c0 = J * TILE;
+        T rr[MT][MT], su[MT][MT], ss[MT][MT], uu[DENSE ? MT : 1][DENSE ? MT : 1];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                rr[i][j] = T(0); su[i][j] = T(0); ss[i][j] = T(0);
+                if (DENSE) uu[i][j] = T(0);
+            }
+        for (int k0 = 0; k0 < d; k0 += KC) {
+            const int kc = min(KC, d - k0);
+            __syncthreads();   // previous chunk / tile fully consumed
+            if (!single_chunk) {
+                stage_tile<T, KC>(a, a.x, t0, k0, kc, xr);
+                stage_tile<T, KC>(a, a.s, t0, k0, kc, sr);
+                if (DENSE) stage_tile<T, KC>(a, a.xl, t0, k0, kc, xlr);
+            }
+            stage_tile<T, KC>(a, a.x, c0, k0, kc, xc);
+            stage_tile<T, KC>(a, a.s, c0, k0, kc, sc);
+            if (DENSE) stage_tile<T, KC>(a, a.xl, c0, k0, kc, xlc);
+            if (k0 == 0 && threadIdx.x < TILE) {
+                const long long t = c0 + threadIdx.x;
+                T v = T(0);
+                if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
+                wc[threadIdx.x] = v;
+            }
+            __syncthreads();
+#pragma unroll 2
+            for (int k = 0; k < kc; ++k) {
+                T xi[MT], si[MT], xj[MT], sj[MT], li[DENSE ? MT : 1], lj[DENSE ? MT : 1];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    xi[i] = xr[k * LD + ty * MT + i];
+                    si[i] = sr[k * LD + ty * MT + i];
+                    xj[i] = xc[k * LD + tx * MT + i];
+                    sj[i] = sc[k * LD + tx * MT + i];
+                    if (DENSE) {
+                        li[i] = xlr[k * LD + ty * MT + i];
+                        lj[i] = xlc[k * LD + tx * MT + i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < MT; ++j) {
+                        const T r = xi[i] - xj[j];
+                        const T ds = si[i] - sj[j];
+                        if (DENSE) {
+                            const T u = li[i] - lj[j];
+                            rr[i][j] = fma_t(u, r, rr[i][j]);
+                            uu[i][j] = fma_t(u, u, uu[i][j]);
+                            su[i][j] = fma_t(ds, u, su[i][j]);
+                        } else {
+                            rr[i][j] = fma_t(r, r, rr[i][j]);
+                            su[i][j] = fma_t(ds, r, su[i][j]);
+                        }
+                        ss[i][j] = fma_t(si[i], sj[j], ss[i][j]);
+                    }
+            }
+        }
+        // epilogue: powers, weights, triangular mask
+        const T lam = T(a.kp.lambda);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const long long t = t0 + ty * MT + i;
+            double part_sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                const long long b = c0 + tx * MT + j;
+                const T qf = DENSE ? (T(a.kp.c) + rr[i][j]) : fma_t(lam, rr[i][j], T(a.kp.c));
+                const T n1 = DENSE ? (T(-3) * uu[i][j]) : (T(-3) * T(a.kp.lambda_sq) * rr[i][j]);
+                const T n2 = DENSE ? (T(a.kp.trace) + su[i][j]) : fma_t(lam, su[i][j], T(a.kp.trace));
+                const T i1 = approx_rsqrt(qf);
+                const T i2 = i1 * i1, i3 = i1 * i2, i5 = i3 * i2;
+                T kv = fma_t(n1, i5, fma_t(n2, i3, ss[i][j] * i1));
+                if (gf) {
+                    const T wi = wr[ty * MT + i], wj = wc[tx * MT + j];
+                    kv *= pre_w ? (wi * wj) : (T)exp((double)wi + (double)wj);
+                }
+                if (b < t && t < a.m) part_sum += (double)kv;
+            }
+            rowacc[i] += part_sum;
+        }
+    }
+    // reduce the TILE/MT threads that share a row (consecutive lanes: tx = lane % 16)
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        double v = rowacc[i];
+#pragma unroll
+        for (int off = (TILE / MT) / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        const long long t = t0 + ty * MT + i;
+        if (tx == 0 && t < a.m) a.low[t] = v;
+    }
+}
+
+// diag[t] = k(t, t) (with weights); rows of tiles owned by other parts are zeroed in low and diag
+template <typename T>
+__global__ void __launch_bounds__(256) ksd_diag_kernel(KsdArgs<T> a) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.m;
+         t += (long long)gridDim.x * blockDim.x) {
+        const bool mine = ((t / TILE) % a.n_parts) == a.part;
+        if (!mine) { a.low[t] = 0.0; a.diag[t] = 0.0; continue; }
+        const long long i = row_of(a, t);
+        const int d = a.kp.d;
+        GView<T> xv{a.x + i * d}, sv{a.s + i * d};
+        T k;
+        if (a.xl) {
+            GView<T> lv{a.xl + i * d};
+            k = pair_fast<T, 0, true>(xv, xv, sv, sv, lv, lv, a.kp);
+        } else {
+            k = pair_fast<T, 0, false>(xv, xv, sv, sv, xv, xv, a.kp);
+        }
+        double kd = (double)k;
+        if (a.lw) {
+            if (a.w) { const T wv = __ldg(a.w + i); kd = (double)(k * (wv * wv)); }
+            else { const double l = (double)__ldg(a.lw + i); kd *= exp(l + l); }
+        }
+        a.diag[t] = kd;
+    }
+}
+
+// ks[t] = sqrt(running sum of 2 low + diag) / (t + 1): sequential scan in index order (numpy's order)
+__global__ void __launch_bounds__(256) ksd_finish_kernel(const double* __restrict__ low,
+                                                         const double* __restrict__ diag, long long m,
+                                                         double* __restrict__ ks) {
+    __shared__ double buf[1024];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = 0.0;
+    for (long long base = 0; base < m; base += 1024) {
+        const int cnt = (int)min(1024LL, m - base);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+            const double l = low[base + e], dg = diag[base + e];
+            buf[e] = (base + e > 0) ? __dadd_rn(__dmul_rn(2.0, l), dg) : dg;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double c = carry;
+            for (int e = 0; e < cnt; ++e) { c = __dadd_rn(c, buf[e]); buf[e] = c; }
+            carry = c;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x)
+            ks[base + e] = __ddiv_rn(__dsqrt_rn(buf[e]), (double)(base + e + 1));
+    }
+}
+
+// ---- element-wise evaluation (integrand protocol, Gram matrix) --------------------------------------
+template <typename T, bool STRICT>
+__device__ __forceinline__ double eval_pair(const KsdArgs<T>& a, long long i, long long j) {
+    const int d = a.kp.d;
+    GView<T> xi{a.x + i * d}, xj{a.x + j * d}, si{a.s + i * d}, sj{a.s + j * d};
+    double k;
+    if constexpr (STRICT) {
+        k = pair_strict<0>(xi, xj, si, sj, a.kp);
+        if (a.lw) k = __dmul_rn(exp(__dadd_rn((double)a.lw[i], (double)a.lw[j])), k);
+    } else {
+        if (a.xl) {
+            GView<T> li{a.xl + i * d}, lj{a.xl + j * d};
+            k = (double)pair_fast<T, 0, true>(xi, xj, si, sj, li, lj, a.kp);
+        } else {
+            k = (double)pair_fast<T, 0, false>(xi, xj, si, sj, xi, xj, a.kp);
+        }
+        if (a.lw) k *= a.w ? (double)(a.w[i] * a.w[j]) : exp((double)a.lw[i] + (double)a.lw[j]);
+    }
+    return k;
+}
+
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(256) pairs_kernel(KsdArgs<T> a, const long long* __restrict__ ia,
+                                                    const long long* __restrict__ ib, long long count,
+                                                    double* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count;
+         e += (long long)gridDim.x * blockDim.x)
+        out[e] = eval_pair<T, STRICT>(a, ia[e], ib[e]);
+}
+
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(256) kmat_kernel(KsdArgs<T> a, double* __restrict__ out) {
+    const long long total = a.m * a.m;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / a.m, c = e - r * a.m;
+        if (c < r) continue;
+        const double k = eval_pair<T, STRICT>(a, row_of(a, r), row_of(a, c));
+        out[r * a.m + c] = k;
+        out[c * a.m + r] = k;
+    }
+}
+
+template <typename T>
+static KsdArgs<T> make_args(const gfk_problem* p, const uint32_t* sel, int64_t m) {
+    KsdArgs<T> a;
+    a.x = static_cast<const T*>(p->x);
+    a.s = static_cast<const T*>(p->s);
+    a.lw = static_cast<const T*>(p->lw);
+    a.w = static_cast<const T*>(p->w);
+    a.xl = static_cast<const T*>(p->xl);
+    a.sel = sel;
+    a.m = m;
+    a.kp = KParams{p->lambda, p->lambda_sq, p->trace, p->c, p->d, p->xl != nullptr};
+    a.part = 0;
+    a.n_parts = 1;
+    a.low = nullptr;
+    a.diag = nullptr;
+    return a;
+}
+
+static int grid1d(long long work) {
+    long long b = (work + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+template <typename T>
+static int rowsums_typed(const gfk_problem* p, const uint32_t* sel, int64_t m, int part, int n_parts, double* low,
+                         double* diag, cudaStream_t st) {
+    KsdArgs<T> a = make_args<T>(p, sel, m);
+    a.part = part;
+    a.n_parts = n_parts;
+    a.low = low;
+    a.diag = diag;
+    ksd_diag_kernel<T><<<grid1d(m), 256, 0, st>>>(a);
+    const long long ntiles = (m + TILE - 1) / TILE;
+    const long long my_tiles = (ntiles - part + n_parts - 1) / n_parts;
+    if (my_tiles > 0) {
+        if (p->xl) {
+            constexpr int KC = 16;
+            const size_t smem = sizeof(T) * (size_t)(6 * KC * LD + 2 * TILE);
+            GFK_CUDA(cudaFuncSetAttribute(ksd_rowsum_kernel<T, true, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+            ksd_rowsum_kernel<T, true, KC><<<(unsigned)my_tiles, KSD_THREADS, smem, st>>>(a);
+        } else {
+            constexpr int KC = 32;
+            const size_t smem = sizeof(T) * (size_t)(4 * KC * LD + 2 * TILE);
+            GFK_CUDA(cudaFuncSetAttribute(ksd_rowsum_kernel<T, false, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+            ksd_rowsum_kernel<T, false, KC><<<(unsigned)my_tiles, KSD_THREADS, smem, st>>>(a);
+        }
+    }
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+static int check_problem(const gfk_problem* p, const char* who) {
+    GFK_REQUIRE(p && p->x && p->s, "%s: NULL problem / x / s", who);
+    GFK_REQUIRE(p->n >= 1 && p->d >= 1, "%s: empty problem", who);
+    GFK_REQUIRE(p->mode >= GFK_F64_STRICT && p->mode <= GFK_F32_FAST, "%s: unknown mode %d", who, p->mode);
+    GFK_REQUIRE(!(p->xl && p->mode == GFK_F64_STRICT), "%s: a dense preconditioner needs a fast mode", who);
+    return GFK_OK;
+}
+
+}  // namespace gfk
+
+using namespace gfk;
+
+extern "C" int gfk_ksd_rowsums(const gfk_problem* p, const uint32_t* sel, int64_t m, int32_t part, int32_t n_parts,
+                               double* low, double* diag, void* stream) {
+    int rc = check_problem(p, "gfk_ksd_rowsums");
+    if (rc) return rc;
+    GFK_REQUIRE(low && diag && m >= 1, "gfk_ksd_rowsums: bad arguments");
+    GFK_REQUIRE(sel || m <= p->n, "gfk_ksd_rowsums: m = %lld exceeds n = %lld", (long long)m, (long long)p->n);
+    GFK_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "gfk_ksd_rowsums: bad part %d of %d", part, n_parts);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the sum order of numpy's ksd() is not reproducible on a GPU, so the strict mode shares the
+    // FMA formulation here (KSD values are checked to 1e-10 relative, not bit for bit)
+    if (p->mode == GFK_F32_FAST) return rowsums_typed<float>(p, sel, m, part, n_parts, low, diag, st);
+    return rowsums_typed<double>(p, sel, m, part, n_parts, low, diag, st);
+}
+
+extern "C" int gfk_ksd_finish(const double* low, const double* diag, int64_t m, double* ks, void* stream) {
+    GFK_REQUIRE(low && diag && ks && m >= 1, "gfk_ksd_finish: bad arguments");
+    ksd_finish_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(low, diag, m, ks);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" int gfk_kmat(const gfk_problem* p, const uint32_t* sel, int64_t m, double* out, void* stream) {
+    int rc = check_problem(p, "gfk_kmat");
+    if (rc) return rc;
+    GFK_REQUIRE(out && m >= 1, "gfk_kmat: bad arguments");
+    GFK_REQUIRE(sel || m <= p->n, "gfk_kmat: m exceeds n");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int g = grid1d(m * m);
+    if (p->mode == GFK_F64_STRICT) kmat_kernel<double, true><<<g, 256, 0, st>>>(make_args<double>(p, sel, m), out);
+    else if (p->mode == GFK_F64_FAST) kmat_kernel<double, false><<<g, 256, 0, st>>>(make_args<double>(p, sel, m), out);
+    else kmat_kernel<float, false><<<g, 256, 0, st>>>(make_args<float>(p, sel, m), out);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" int gfk_pairs(const gfk_problem* p, const int64_t* ia, const int64_t* ib, int64_t count, double* out,
+                         void* stream) {
+    int rc = check_problem(p, "gfk_pairs");
+    if (rc) return rc;
+    GFK_REQUIRE(ia && ib && out && count >= 0, "gfk_pairs: bad arguments");
+    if (count == 0) return GFK_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int g = grid1d(count);
+    const long long* a64 = reinterpret_cast<const long long*>(ia);
+    const long long* b64 = reinterpret_cast<const long long*>(ib);
+    if (p->mode == GFK_F64_STRICT)
+        pairs_kernel<double, true><<<g, 256, 0, st>>>(make_args<double>(p, nullptr, 0), a64, b64, count, out);
+    else if (p->mode == GFK_F64_FAST)
+        pairs_kernel<double, false><<<g, 256, 0, st>>>(make_args<double>(p, nullptr, 0), a64, b64, count, out);
+    else
+        pairs_kernel<float, false><<<g, 256, 0, st>>>(make_args<float>(p, nullptr, 0), a64, b64, count, out);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}

@@ -1,0 +1,355 @@
+// prep.cu - the O(n d) passes in front of the pair kernels.
+//
+//   gfk_standardize   : stein_thinning.thinning._validate_and_standardize
+//                       (call site code/notebooks/examples/JAX_Stein_Thinning.ipynb#c16;
+//                        scale = mean absolute deviation)
+//   gfk_median_pdist  : the 'med' rule of stein_thinning.kernel.make_precon
+//                       (report/report.tex:323,435; call site JAX_Stein_Thinning.ipynb#c28)
+//   gfk_exp_weights / gfk_to_f32 / gfk_check_finite : small element-wise helpers
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace gfk {
+
+constexpr int kChunkRows = 2048;
+constexpr int kRedThreads = 256;
+
+struct StdWs {
+    unsigned long long nonfinite;
+    // followed by: loc[d], scl[d], partial[nchunks][d]
+};
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < kRedThreads / 32; ++w) r += sh[w];
+    }
+    return r;  // valid in thread 0
+}
+
+// pass A (absdev == 0): partial[c][k] = sum over the chunk of x[r][k]; counts non-finite x
+// pass B (absdev == 1): partial[c][k] = sum over the chunk of |x[r][k] - loc[k]|
+__global__ void __launch_bounds__(kRedThreads) col_chunk_sum_kernel(const double* __restrict__ x, long long n,
+                                                                    int d, int absdev,
+                                                                    const double* __restrict__ loc,
+                                                                    double* __restrict__ partial,
+                                                                    unsigned long long* nonfinite) {
+    __shared__ double sh[kRedThreads / 32];
+    const long long r0 = (long long)blockIdx.x * kChunkRows;
+    const long long r1 = min(n, r0 + kChunkRows);
+    unsigned bad = 0;
+    for (int k = 0; k < d; ++k) {
+        const double lk = absdev ? loc[k] : 0.0;
+        double acc = 0.0;
+        for (long long r = r0 + threadIdx.x; r < r1; r += kRedThreads) {
+            const double v = x[r * d + k];
+            if (!absdev && !isfinite(v)) ++bad;
+            acc += absdev ? fabs(v - lk) : v;
+        }
+        const double tot = block_sum_256(acc, sh);
+        if (threadIdx.x == 0) partial[(long long)blockIdx.x * d + k] = tot;
+    }
+    if (bad) atomicAdd(nonfinite, (unsigned long long)bad);
+}
+
+// out[k] = (sum of the chunk partials in index order) / n
+__global__ void col_finish_kernel(const double* __restrict__ partial, int nchunks, int d, long long n,
+                                  double* __restrict__ out) {
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        double acc = 0.0;
+        for (int c = 0; c < nchunks; ++c) acc += partial[(long long)c * d + k];
+        out[k] = acc / (double)n;
+    }
+}
+
+// x_out = x / scl, g_out = g * scl (IEEE division / multiplication, as numpy); counts non-finite g
+__global__ void __launch_bounds__(256) scale_kernel(const double* __restrict__ x, const double* __restrict__ g,
+                                                    long long count, int d, const double* __restrict__ scl,
+                                                    int standardize, double* __restrict__ x_out,
+                                                    double* __restrict__ g_out, unsigned long long* nonfinite) {
+    unsigned bad = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % d);
+        const double xv = x[e], gv = g[e];
+        if (!isfinite(gv)) ++bad;
+        if (standardize) {
+            const double sc = scl[k];
+            x_out[e] = __ddiv_rn(xv, sc);
+            g_out[e] = __dmul_rn(gv, sc);
+        } else {
+            x_out[e] = xv;
+            g_out[e] = gv;
+        }
+    }
+    if (bad) atomicAdd(nonfinite, (unsigned long long)bad);
+}
+
+// ---- median of pairwise distances ----------------------------------------------------------------
+// dist[p] for the p-th pair (i < j) in condensed order, scipy's euclidean: s += (u-v)*(u-v); sqrt(s)
+__global__ void __launch_bounds__(256) pdist_kernel(const double* __restrict__ x, const long long* __restrict__ rows,
+                                                    int R, int d, double* __restrict__ dist) {
+    const long long npairs = (long long)R * (R - 1) / 2;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npairs;
+         p += (long long)gridDim.x * blockDim.x) {
+        // invert p -> (i, j): pairs before row i: i*R - i*(i+1)/2
+        long long i = (long long)floor(((2.0 * R - 1.0) - sqrt((2.0 * R - 1.0) * (2.0 * R - 1.0) - 8.0 * (double)p)) * 0.5);
+        while (i > 0 && i * R - i * (i + 1) / 2 > p) --i;
+        while ((i + 1) * R - (i + 1) * (i + 2) / 2 <= p) ++i;
+        const long long j = p - (i * R - i * (i + 1) / 2) + i + 1;
+        const double* u = x + rows[i] * d;
+        const double* v = x + rows[j] * d;
+        double s = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double t = __dsub_rn(u[k], v[k]);
+            s = __dadd_rn(s, __dmul_rn(t, t));
+        }
+        dist[p] = __dsqrt_rn(s);
+    }
+}
+
+// radix select on the bit patterns of non-negative doubles: block b finds order statistic rank[b]
+__global__ void __launch_bounds__(1024) radix_select_kernel(const double* __restrict__ dist, long long count,
+                                                            long long rank0, long long rank1,
+                                                            double* __restrict__ out) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long prefix_sh;
+    __shared__ long long rank_sh;
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(dist);
+    if (threadIdx.x == 0) {
+        prefix_sh = 0ull;
+        rank_sh = blockIdx.x == 0 ? rank0 : rank1;
+    }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned long long prefix = prefix_sh;
+        const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+        for (long long e = threadIdx.x; e < count; e += blockDim.x) {
+            const unsigned long long key = keys[e];
+            if ((key & himask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & 0xffu)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long r = rank_sh;
+            int b = 0;
+            for (; b < 256; ++b) {
+                if (r < (long long)hist[b]) break;
+                r -= hist[b];
+            }
+            rank_sh = r;
+            prefix_sh = prefix | ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = __longlong_as_double((long long)prefix_sh);
+}
+
+__global__ void to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, long long count) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count;
+         e += (long long)gridDim.x * blockDim.x)
+        dst[e] = (float)src[e];
+}
+
+template <typename T>
+__global__ void exp_weights_kernel(const T* __restrict__ lw, T* __restrict__ w, long long count) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count;
+         e += (long long)gridDim.x * blockDim.x)
+        w[e] = (T)exp((double)lw[e]);
+}
+
+// lw = log_q - log_p; optional range cap: lw = max(lw - max(lw), -cap).  Two launches: (min, max, NaN) then apply.
+__global__ void __launch_bounds__(256) lw_minmax_kernel(const double* __restrict__ log_p,
+                                                        const double* __restrict__ log_q, long long n,
+                                                        double* __restrict__ stats /* [gridDim][3] */) {
+    __shared__ double sh_min[8], sh_max[8], sh_bad[8];
+    double mn = INFINITY, mx = -INFINITY, bad = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const double a = log_p[e], b = log_q[e];
+        if (isnan(a) || isnan(b)) bad += 1.0;
+        const double v = __dsub_rn(b, a);
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        bad += __shfl_xor_sync(0xffffffffu, bad, off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh_min[warp] = mn; sh_max[warp] = mx; sh_bad[warp] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = fmin(mn, sh_min[w]); mx = fmax(mx, sh_max[w]); bad += sh_bad[w]; }
+        stats[blockIdx.x * 3 + 0] = mn;
+        stats[blockIdx.x * 3 + 1] = mx;
+        stats[blockIdx.x * 3 + 2] = bad;
+    }
+}
+
+__global__ void lw_apply_kernel(const double* __restrict__ log_p, const double* __restrict__ log_q, long long n,
+                                int use_cap, double mx, double cap, double* __restrict__ lw) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        double v = __dsub_rn(log_q[e], log_p[e]);
+        if (use_cap) v = fmax(__dsub_rn(v, mx), -cap);
+        lw[e] = v;
+    }
+}
+
+static int grid_for(long long work, int threads) {
+    long long b = (work + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace gfk
+
+using namespace gfk;
+
+extern "C" size_t gfk_standardize_ws_bytes(int64_t n, int32_t d) {
+    const int64_t nchunks = (n + kChunkRows - 1) / kChunkRows;
+    return 64 + sizeof(double) * (size_t)(2 * (int64_t)d + nchunks * d);
+}
+
+extern "C" int gfk_standardize(const double* x, const double* g, int64_t n, int32_t d, int standardize,
+                               double* x_out, double* g_out, double* scl_host, void* ws, void* stream) {
+    GFK_REQUIRE(x && g && x_out && g_out && scl_host && ws, "gfk_standardize: NULL pointer argument");
+    GFK_REQUIRE(n >= 1 && d >= 1, "gfk_standardize: empty sample (n = %lld, d = %d)", (long long)n, d);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long* nonfinite = reinterpret_cast<unsigned long long*>(ws);
+    double* loc = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 64);
+    double* scl = loc + d;
+    double* partial = scl + d;
+    const int nchunks = (int)((n + kChunkRows - 1) / kChunkRows);
+    GFK_CUDA(cudaMemsetAsync(nonfinite, 0, 64, st));
+    col_chunk_sum_kernel<<<nchunks, kRedThreads, 0, st>>>(x, n, d, 0, nullptr, partial, nonfinite);
+    col_finish_kernel<<<1, 128, 0, st>>>(partial, nchunks, d, n, loc);
+    if (standardize) {
+        col_chunk_sum_kernel<<<nchunks, kRedThreads, 0, st>>>(x, n, d, 1, loc, partial, nonfinite);
+        col_finish_kernel<<<1, 128, 0, st>>>(partial, nchunks, d, n, scl);
+    }
+    scale_kernel<<<grid_for(n * d, 256), 256, 0, st>>>(x, g, n * d, d, scl, standardize, x_out, g_out, nonfinite);
+    GFK_CHECK_LAUNCH();
+    unsigned long long bad = 0;
+    GFK_CUDA(cudaMemcpyAsync(&bad, nonfinite, sizeof(bad), cudaMemcpyDeviceToHost, st));
+    if (standardize) {
+        GFK_CUDA(cudaMemcpyAsync(scl_host, scl, sizeof(double) * d, cudaMemcpyDeviceToHost, st));
+    }
+    GFK_CUDA(cudaStreamSynchronize(st));
+    if (!standardize) for (int k = 0; k < d; ++k) scl_host[k] = 1.0;
+    if (bad) {
+        set_error("sample or gradient contains NaNs or infs (%llu entries)", bad);
+        return GFK_ENUMERIC;
+    }
+    if (standardize) {
+        for (int k = 0; k < d; ++k) {
+            if (!(scl_host[k] > 0.0)) {
+                set_error("Too few unique samples in sample (column %d has zero mean absolute deviation).", k);
+                return GFK_ENUMERIC;
+            }
+        }
+    }
+    return GFK_OK;
+}
+
+extern "C" size_t gfk_median_ws_bytes(int64_t n, int32_t cap) {
+    const int64_t R = n > cap ? cap : n;
+    return 64 + sizeof(long long) * (size_t)R + sizeof(double) * (size_t)(R * (R - 1) / 2 + 2);
+}
+
+extern "C" int gfk_median_pdist(const double* x, int64_t n, int32_t d, int32_t cap, double* mid_host, void* ws,
+                                void* stream) {
+    GFK_REQUIRE(x && mid_host && ws, "gfk_median_pdist: NULL pointer argument");
+    GFK_REQUIRE(n >= 2 && d >= 1 && cap >= 2, "gfk_median_pdist: need n >= 2, d >= 1, cap >= 2");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int R = (int)(n > cap ? cap : n);
+    // rows = np.linspace(0, n - 1, cap, dtype=int) when n > cap (numpy: arange(num) * step, last = stop)
+    std::vector<long long> rows(R);
+    if (n > cap) {
+        const double step = (double)(n - 1) / (double)(cap - 1);
+        for (int a = 0; a < R; ++a) rows[a] = (long long)((double)a * step);
+        rows[R - 1] = n - 1;
+    } else {
+        for (int a = 0; a < R; ++a) rows[a] = a;
+    }
+    double* out2 = reinterpret_cast<double*>(ws);  // two order statistics
+    long long* rows_dev = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 64);
+    double* dist = reinterpret_cast<double*>(rows_dev + R);
+    // keep dist 8-byte aligned (rows_dev is 8-byte elements at a 64-byte offset)
+    GFK_CUDA(cudaMemcpyAsync(rows_dev, rows.data(), sizeof(long long) * R, cudaMemcpyHostToDevice, st));
+    const long long npairs = (long long)R * (R - 1) / 2;
+    pdist_kernel<<<grid_for(npairs, 256), 256, 0, st>>>(x, rows_dev, R, d, dist);
+    // np.median: mean of the two middle order statistics (equal ranks when the count is odd)
+    const long long k1 = npairs / 2;
+    const long long k0 = (npairs % 2 == 0) ? k1 - 1 : k1;
+    radix_select_kernel<<<2, 1024, 0, st>>>(dist, npairs, k0, k1, out2);
+    GFK_CHECK_LAUNCH();
+    GFK_CUDA(cudaMemcpyAsync(mid_host, out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GFK_CUDA(cudaStreamSynchronize(st));  // also keeps `rows` alive until the copy has been consumed
+    return GFK_OK;
+}
+
+extern "C" int gfk_to_f32(const double* src, float* dst, int64_t count, void* stream) {
+    GFK_REQUIRE(src && dst && count >= 0, "gfk_to_f32: bad arguments");
+    if (count == 0) return GFK_OK;
+    to_f32_kernel<<<grid_for(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, count);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f32, void* stream) {
+    GFK_REQUIRE(lw && w && count >= 0, "gfk_exp_weights: bad arguments");
+    if (count == 0) return GFK_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (is_f32)
+        exp_weights_kernel<float><<<grid_for(count, 256), 256, 0, st>>>(static_cast<const float*>(lw),
+                                                                        static_cast<float*>(w), count);
+    else
+        exp_weights_kernel<double><<<grid_for(count, 256), 256, 0, st>>>(static_cast<const double*>(lw),
+                                                                         static_cast<double*>(w), count);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" size_t gfk_log_weights_ws_bytes(void) { return sizeof(double) * 3 * 1024; }
+
+extern "C" int gfk_log_weights(const double* log_p, const double* log_q, int64_t n, int use_cap, double range_cap,
+                               double* lw, double* spread_host, void* ws, void* stream) {
+    GFK_REQUIRE(log_p && log_q && lw && spread_host && ws && n >= 1, "gfk_log_weights: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int grid = grid_for(n, 256);
+    if (grid > 1024) grid = 1024;
+    double* stats = static_cast<double*>(ws);
+    lw_minmax_kernel<<<grid, 256, 0, st>>>(log_p, log_q, n, stats);
+    GFK_CHECK_LAUNCH();
+    std::vector<double> h(3 * (size_t)grid);
+    GFK_CUDA(cudaMemcpyAsync(h.data(), stats, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    GFK_CUDA(cudaStreamSynchronize(st));
+    double mn = INFINITY, mx = -INFINITY, bad = 0.0;
+    for (int b = 0; b < grid; ++b) {
+        mn = fmin(mn, h[3 * b]);
+        mx = fmax(mx, h[3 * b + 1]);
+        bad += h[3 * b + 2];
+    }
+    if (bad > 0.0) {
+        set_error("log-densities contain NaNs (%g entries)", bad);
+        return GFK_ENUMERIC;
+    }
+    *spread_host = mx - mn;
+    lw_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(log_p, log_q, n, use_cap, mx, range_cap, lw);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}

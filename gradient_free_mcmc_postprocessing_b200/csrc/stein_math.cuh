@@ -1,0 +1,233 @@
+// stein_math.cuh - the pair kernel k(x, y) of the Stein thinning / GF-KSD path.
+//
+// Replaces stein_thinning.kernel.vfk0_imq (restated in the reference at
+// code/notebooks/examples/JAX_Stein_Thinning.ipynb#c27 and, term by term, at
+// code/notebooks/Kernel_Stein_discrepancy.ipynb#c7; derivation report/report.tex:853-868)
+// with c = 1 and beta = -1/2 (report/report.tex:435), for the scalar preconditioner
+// Gamma^-1 = lambda * I and, through a pre-multiplied copy xl = x @ L, a dense symmetric one.
+//
+//   r = x - y,  qf = c + lambda |r|^2
+//   k = -3 lambda^2 |r|^2 / qf^2.5 + (tr + lambda <sx - sy, r>) / qf^1.5 + <sx, sy> / qf^0.5
+//
+// Two formulations, both plain scalar code so the same header also compiles for the host
+// (tests/host/pair_check.cpp checks the strict path against numpy bit for bit on the CPU):
+//
+//   strict : numpy's operation order, no FMA contraction, correctly rounded sqrt / powers /
+//            divisions.  Every operation except pow() and exp() is reproduced bit for bit;
+//            pow(q, 1.5 | 2.5) is computed correctly rounded from a double-double sqrt
+//            (numpy's own SVML pow is correctly rounded in ~95 % of cases, glibc's in 99.9 %).
+//   fast   : FMA sums, one rsqrt, r, r^3, r^5 by multiplication.  <= a few ulp from strict.
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define GFK_HD __host__ __device__ __forceinline__
+#else
+#define GFK_HD inline
+#endif
+
+namespace gfk {
+
+struct KParams {
+    double lambda;     // Gamma^-1 = lambda * I
+    double lambda_sq;  // fl(lambda * lambda), numpy's np.dot(linv, linv) diagonal
+    double trace;      // np.trace(linv)
+    double c;          // IMQ constant (1.0)
+    int d;             // runtime dimension (used when the template D is 0)
+    int dense;         // 1: dense L through the pre-multiplied copy xl (fast formulation only)
+};
+
+// ---- non-contracted IEEE operations ------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+GFK_HD double nf_mul(double a, double b) { return __dmul_rn(a, b); }
+GFK_HD double nf_add(double a, double b) { return __dadd_rn(a, b); }
+GFK_HD double nf_sub(double a, double b) { return __dsub_rn(a, b); }
+GFK_HD double nf_sqrt(double a) { return __dsqrt_rn(a); }
+GFK_HD double nf_div(double a, double b) { return __ddiv_rn(a, b); }
+GFK_HD double nf_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+GFK_HD double approx_rsqrt(double a) { return rsqrt(a); }
+GFK_HD float approx_rsqrt(float a) { return rsqrtf(a); }
+#else
+// host build: compiled with -ffp-contract=off so a * b + c stays two roundings
+GFK_HD double nf_mul(double a, double b) { return a * b; }
+GFK_HD double nf_add(double a, double b) { return a + b; }
+GFK_HD double nf_sub(double a, double b) { return a - b; }
+GFK_HD double nf_sqrt(double a) { return sqrt(a); }
+GFK_HD double nf_div(double a, double b) { return a / b; }
+GFK_HD double nf_fma(double a, double b, double c) { return fma(a, b, c); }
+GFK_HD double approx_rsqrt(double a) { return 1.0 / sqrt(a); }
+GFK_HD float approx_rsqrt(float a) { return 1.0f / sqrtf(a); }
+#endif
+
+GFK_HD double fma_t(double a, double b, double c) { return nf_fma(a, b, c); }
+GFK_HD float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+
+// q^0.5 (correctly rounded), q^1.5 and q^2.5 (correctly rounded up to ~2^-100) for q >= 0.
+// sqrt(q) = s + sl with s = RN(sqrt q), sl = (q - s*s) / (2 s); the products q * (s + sl) and
+// q^2 * (s + sl) are formed in double-double and rounded once.
+GFK_HD void strict_powers(double q, double& p05, double& p15, double& p25) {
+    const double s = nf_sqrt(q);
+    p05 = s;
+    const double resid = nf_fma(-s, s, q);                 // exact: q - s*s
+    const double sl = (s > 0.0) ? nf_mul(resid, nf_mul(0.5, approx_rsqrt(q))) : 0.0;
+    // q^1.5
+    const double h1 = nf_mul(q, s);
+    double l1 = nf_fma(q, s, -h1);                         // exact low part of q*s
+    l1 = nf_fma(q, sl, l1);
+    p15 = nf_add(h1, l1);
+    // q^2.5
+    const double qh = nf_mul(q, q);
+    const double ql = nf_fma(q, q, -qh);                   // exact low part of q*q
+    const double h2 = nf_mul(qh, s);
+    double l2 = nf_fma(qh, s, -h2);
+    l2 = nf_fma(qh, sl, l2);
+    l2 = nf_fma(ql, s, l2);
+    p25 = nf_add(h2, l2);
+    if (!(fabs(h1) < 1.0e300)) p15 = h1;                   // overflow / inf / nan: plain product
+    if (!(fabs(h2) < 1.0e300)) p25 = h2;
+}
+
+// numpy's pairwise summation of the d products sx_k * sy_k (np.sum over the contiguous
+// axis of an F-ordered (d, n) array; numpy/_core/src/umath/loops_utils.h.src, pairwise_sum):
+// plain loop for d < 8, eight strided accumulators combined as a tree for d <= 128,
+// recursive halving (multiple of 8) above.  STRIDE lets the caller pass SoA / padded rows.
+template <typename AX, typename AY>
+GFK_HD double pairwise_dot_block(const AX& sx, const AY& sy, int lo, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = nf_add(res, nf_mul(sx[lo + i], sy[lo + i]));
+        return res;
+    }
+    double r0 = nf_mul(sx[lo + 0], sy[lo + 0]), r1 = nf_mul(sx[lo + 1], sy[lo + 1]);
+    double r2 = nf_mul(sx[lo + 2], sy[lo + 2]), r3 = nf_mul(sx[lo + 3], sy[lo + 3]);
+    double r4 = nf_mul(sx[lo + 4], sy[lo + 4]), r5 = nf_mul(sx[lo + 5], sy[lo + 5]);
+    double r6 = nf_mul(sx[lo + 6], sy[lo + 6]), r7 = nf_mul(sx[lo + 7], sy[lo + 7]);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+        r0 = nf_add(r0, nf_mul(sx[lo + i + 0], sy[lo + i + 0]));
+        r1 = nf_add(r1, nf_mul(sx[lo + i + 1], sy[lo + i + 1]));
+        r2 = nf_add(r2, nf_mul(sx[lo + i + 2], sy[lo + i + 2]));
+        r3 = nf_add(r3, nf_mul(sx[lo + i + 3], sy[lo + i + 3]));
+        r4 = nf_add(r4, nf_mul(sx[lo + i + 4], sy[lo + i + 4]));
+        r5 = nf_add(r5, nf_mul(sx[lo + i + 5], sy[lo + i + 5]));
+        r6 = nf_add(r6, nf_mul(sx[lo + i + 6], sy[lo + i + 6]));
+        r7 = nf_add(r7, nf_mul(sx[lo + i + 7], sy[lo + i + 7]));
+    }
+    double res = nf_add(nf_add(nf_add(r0, r1), nf_add(r2, r3)), nf_add(nf_add(r4, r5), nf_add(r6, r7)));
+    for (; i < n; ++i) res = nf_add(res, nf_mul(sx[lo + i], sy[lo + i]));
+    return res;
+}
+
+template <typename AX, typename AY>
+GFK_HD double pairwise_dot(const AX& sx, const AY& sy, int d) {
+    if (d <= 128) return nf_add(0.0, pairwise_dot_block(sx, sy, 0, d));
+    // iterative form of numpy's recursion: split [lo, lo + n) at n2 = (n / 2) rounded down to 8
+    // until blocks are <= 128, summing leaves in recursion order with an explicit stack
+    int lo_stack[24], n_stack[24];
+    double val_stack[24];
+    int state[24];
+    int sp = 0;
+    lo_stack[0] = 0; n_stack[0] = d; state[0] = 0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int n = n_stack[sp], lo = lo_stack[sp];
+        if (n <= 128) { ret = pairwise_dot_block(sx, sy, lo, n); --sp; continue; }
+        int n2 = n / 2; n2 -= n2 % 8;
+        if (state[sp] == 0) {          // descend left
+            state[sp] = 1; ++sp; lo_stack[sp] = lo; n_stack[sp] = n2; state[sp] = 0;
+        } else if (state[sp] == 1) {   // left done, descend right
+            val_stack[sp] = ret; state[sp] = 2; ++sp; lo_stack[sp] = lo + n2; n_stack[sp] = n - n2; state[sp] = 0;
+        } else {                       // both done
+            ret = nf_add(val_stack[sp], ret); --sp;
+        }
+    }
+    return nf_add(0.0, ret);
+}
+
+// ---- strict pair kernel (float64) ------------------------------------------------------------
+// x, y, sx, sy: anything indexable by [k] (register arrays, strided shared-memory views).
+// Returns k(x, y) WITHOUT the gradient-free weight.
+template <int D, typename AX, typename AY, typename ASX, typename ASY>
+GFK_HD double pair_strict(const AX& x, const AY& y, const ASX& sx, const ASY& sy, const KParams& kp) {
+    const int d = D > 0 ? D : kp.d;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        const double r = nf_sub(x[k], y[k]);
+        const double a = nf_mul(nf_mul(kp.lambda, r), r);
+        const double b = nf_mul(nf_mul(kp.lambda_sq, r), r);
+        const double cc = nf_mul(nf_mul(kp.lambda, nf_sub(sx[k], sy[k])), r);
+        if (k == 0) { s1 = a; s2 = b; s3 = cc; }
+        else { s1 = nf_add(s1, a); s2 = nf_add(s2, b); s3 = nf_add(s3, cc); }
+    }
+    double s4;
+    if (d < 8) {
+        s4 = 0.0;
+#pragma unroll
+        for (int k = 0; k < d; ++k) {
+            const double p = nf_mul(sx[k], sy[k]);
+            s4 = (k == 0) ? p : nf_add(s4, p);
+        }
+    } else {
+        s4 = pairwise_dot(sx, sy, d);
+    }
+    const double qf = nf_add(kp.c, s1);
+    double p05, p15, p25;
+    strict_powers(qf, p05, p15, p25);
+    const double t1 = nf_div(nf_mul(-3.0, s2), p25);
+    const double t2 = nf_div(nf_add(kp.trace, s3), p15);
+    const double t3 = nf_div(s4, p05);
+    return nf_add(nf_add(t1, t2), t3);
+}
+
+// ---- fast pair kernel (float64 or float32) ------------------------------------------------------
+// xl == x for the scalar preconditioner; for a dense symmetric L the caller passes the
+// pre-multiplied rows xl = x @ L, yl = y @ L and kp.lambda = kp.lambda_sq = 1:
+//   u = xl - yl = L r;  qf = c + <u, r>;  |L r|^2 = <u, u>;  <L (sx - sy), r> = <sx - sy, u>.
+template <typename T, int D, bool DENSE, typename AX, typename AY, typename ASX, typename ASY, typename AXL,
+          typename AYL>
+GFK_HD T pair_fast(const AX& x, const AY& y, const ASX& sx, const ASY& sy, const AXL& xl, const AYL& yl,
+                   const KParams& kp) {
+    const int d = D > 0 ? D : kp.d;
+    T rr = T(0), uu = T(0), su = T(0), ss = T(0);
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        const T r = T(x[k]) - T(y[k]);
+        const T ds = T(sx[k]) - T(sy[k]);
+        if (DENSE) {
+            const T u = T(xl[k]) - T(yl[k]);
+            rr = fma_t(u, r, rr);
+            uu = fma_t(u, u, uu);
+            su = fma_t(ds, u, su);
+        } else {
+            rr = fma_t(r, r, rr);
+            su = fma_t(ds, r, su);
+        }
+        ss = fma_t(T(sx[k]), T(sy[k]), ss);
+    }
+    const T lam = T(kp.lambda);
+    const T qf = DENSE ? (T(kp.c) + rr) : fma_t(lam, rr, T(kp.c));
+    const T n1 = DENSE ? (T(-3) * uu) : (T(-3) * T(kp.lambda_sq) * rr);
+    const T n2 = DENSE ? (T(kp.trace) + su) : fma_t(lam, su, T(kp.trace));
+    const T i1 = approx_rsqrt(qf);
+    const T i2 = i1 * i1;
+    const T i3 = i1 * i2;
+    const T i5 = i3 * i2;
+    return fma_t(n1, i5, fma_t(n2, i3, ss * i1));
+}
+
+// ---- (value, index) with numpy.argmin semantics ---------------------------------------------------
+// smaller value wins; NaN beats every number (np.argmin returns the first NaN); ties -> lower index
+struct Cand {
+    double v;
+    unsigned long long i;
+};
+
+GFK_HD bool cand_better(double va, unsigned long long ia, double vb, unsigned long long ib) {
+    const bool na = (va != va), nb = (vb != vb);
+    if (na || nb) return (na && !nb) || (na && nb && ia < ib);
+    return (va < vb) || (va == vb && ia < ib);
+}
+
+}  // namespace gfk

@@ -1,0 +1,83 @@
+"""The integrand protocol of ``stein_thinning`` (``integrand(ind1, ind2) -> ndarray``), device backed.
+
+Reference: the closures returned by ``_make_stein_integrand`` / ``_make_stein_gf_integrand``
+(code/notebooks/examples/JAX_Stein_Thinning.ipynb#c17; code/src/utils/ksd.py:9-16;
+code/tests/test_ksd.py:16-20).  Index arguments may be ``slice(None)``, lists or arrays and
+broadcast against each other like numpy fancy indexing of the paired rows.
+"""
+import numpy as np
+
+
+def _expand(index, n):
+    if isinstance(index, slice):
+        return np.arange(n)[index]
+    return np.asarray(index, dtype=np.int64)
+
+
+class SteinIntegrand:
+    """Callable integrand whose pair evaluations, greedy search, KSD and Gram matrix run in libgfk."""
+
+    def __init__(self, problem, indices=None):
+        self.problem = problem
+        self.indices = None if indices is None else np.asarray(indices, dtype=np.int64)
+
+    @property
+    def n(self):
+        return self.problem.n if self.indices is None else len(self.indices)
+
+    def __call__(self, ind1, ind2):
+        a, b = np.broadcast_arrays(_expand(ind1, self.n), _expand(ind2, self.n))
+        if self.indices is not None:
+            a, b = self.indices[a], self.indices[b]
+        return self.problem.pairs(a, b)
+
+    def reindex(self, indices):
+        indices = np.asarray(indices, dtype=np.int64)
+        return SteinIntegrand(self.problem, indices if self.indices is None else self.indices[indices])
+
+    def thin(self, n_points):
+        if self.indices is not None:
+            raise NotImplementedError('greedy search over a re-indexed integrand is not part of the reference path')
+        return self.problem.thin(n_points)
+
+    def ksd(self, n):
+        if self.indices is None:
+            return self.problem.ksd(None, n)
+        return self.problem.ksd(self.indices[:n], n)
+
+    def kmat(self, n):
+        if self.indices is None:
+            return self.problem.kmat(None, n)
+        return self.problem.kmat(self.indices[:n], n)
+
+
+# ---- foreign callables: the protocol itself, driven on the host ---------------------------------------
+# These loops contain no kernel arithmetic: every value comes from the caller's own integrand.
+
+def greedy_search_callable(n_points, integrand):
+    idx = np.empty(n_points, dtype=np.uint32)
+    running = np.array(integrand(slice(None), slice(None)), dtype=float)
+    idx[0] = np.argmin(running)
+    for i in range(1, n_points):
+        running += 2 * np.asarray(integrand(slice(None), [idx[i - 1]]))
+        idx[i] = np.argmin(running)
+    return idx
+
+
+def kmat_callable(integrand, n):
+    rows, cols = np.triu_indices(n)
+    upper = np.asarray(integrand(rows, cols))
+    out = np.zeros((n, n), dtype=upper.dtype)
+    out[rows, cols] = upper
+    out[cols, rows] = upper
+    return out
+
+
+def ksd_callable(integrand, n):
+    ks = np.empty(n)
+    total = 0.0
+    for t in range(n):
+        diag = np.asarray(integrand([t], [t])).reshape(-1)[0]
+        total += (2 * np.sum(integrand(np.arange(t), [t])) + diag) if t > 0 else diag
+        ks[t] = np.sqrt(total) / (t + 1)
+    return ks

@@ -1,0 +1,71 @@
+"""``stein_thinning.thinning`` + the reference's ``code/src/thinning.py`` on the B200.
+
+Same names, positional order and defaults as the reference's call sites
+(``thin``: Gradient_free_Stein_thinning.ipynb#c8, Gaussian_mixture.ipynb#c28;
+``thin_gf``: code/src/thinning.py:17, Gaussian_mixture.ipynb#c39;
+``_make_stein_integrand``: code/src/utils/ksd.py:25; ``_greedy_search``:
+JAX_Stein_Thinning.ipynb#c18,#c22; ``gaussian_thin``: code/src/thinning.py:14-17).
+Two keyword-only extensions: ``precision`` ('f64' strict parity mode [default], 'f64-fast',
+'f32') and ``device``.
+"""
+import numpy as np
+import torch
+
+from ._engine import WEIGHT_SCALE_THRESHOLD, SteinProblem  # noqa: F401
+from .integrand import SteinIntegrand, greedy_search_callable
+
+
+def _validate_and_standardize(sample, gradient, standardize, *, device=None):
+    """Returns the (standardised) sample and gradient as numpy arrays, computed on the device."""
+    prob = SteinProblem(sample, gradient, standardize=standardize, preconditioner='id', precision='f64',
+                        device=device)
+    return prob.x.cpu().numpy(), prob.s.cpu().numpy()
+
+
+def _make_stein_integrand(sample, gradient, standardize=True, preconditioner='id', *, precision=None,
+                          device=None):
+    return SteinIntegrand(SteinProblem(sample, gradient, standardize=standardize,
+                                       preconditioner=preconditioner, precision=precision, device=device))
+
+
+def _make_stein_gf_integrand(sample, log_p, log_q, gradient_q, standardize=True, preconditioner='id',
+                             range_cap=None, *, precision=None, device=None):
+    return SteinIntegrand(SteinProblem(sample, gradient_q, log_p=log_p, log_q=log_q, standardize=standardize,
+                                       preconditioner=preconditioner, range_cap=range_cap,
+                                       precision=precision, device=device))
+
+
+def _greedy_search(n_points, integrand):
+    """Greedy selection.  A ``SteinIntegrand`` runs fused on the GPU; any other callable obeying the
+    integrand protocol is driven on the host exactly like the reference loop (its arithmetic is the
+    callable's own, e.g. the fake integrand of code/tests/test_ksd.py)."""
+    if isinstance(integrand, SteinIntegrand):
+        return integrand.thin(n_points)
+    return greedy_search_callable(n_points, integrand)
+
+
+def thin(sample, gradient, n_points, standardize=True, preconditioner='id', *, precision=None, device=None):
+    integrand = _make_stein_integrand(sample, gradient, standardize, preconditioner, precision=precision,
+                                      device=device)
+    return _greedy_search(n_points, integrand)
+
+
+def thin_gf(sample, log_p, log_q, gradient_q, n_points, standardize=True, preconditioner='id', range_cap=None,
+            *, precision=None, device=None):
+    integrand = _make_stein_gf_integrand(sample, log_p, log_q, gradient_q, standardize, preconditioner,
+                                         range_cap, precision=precision, device=device)
+    return _greedy_search(n_points, integrand)
+
+
+def gaussian_thin(sample, log_p, mean, cov, thinned_size, range_cap=200, *, precision=None, device=None):
+    """Gaussian-proxy gradient-free thinning (reference: code/src/thinning.py:14-17).
+
+    The proxy's log-density and score are O(n d^2) host-side numpy here exactly as in the reference
+    (scipy ``mvn.logpdf`` + einsum); moving them onto the device is SURVEY.md section 8f item 1.
+    """
+    from scipy.stats import multivariate_normal as mvn
+    sample_np = sample.cpu().numpy() if isinstance(sample, torch.Tensor) else np.asarray(sample)
+    log_q = mvn.logpdf(sample_np, mean=mean, cov=cov)
+    gradient_q = -np.einsum('ij,kj->ki', np.linalg.inv(cov), sample_np - mean)
+    return thin_gf(sample, log_p, log_q, gradient_q, thinned_size, range_cap=range_cap, preconditioner='med',
+                   precision=precision, device=device)

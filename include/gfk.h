@@ -1,0 +1,162 @@
+/*
+ * gfk.h - C ABI of libgfk: B200 (sm_100a) Stein thinning / gradient-free KSD.
+ *
+ * The reference (aglebov/gradient-free-mcmc-postprocessing) has no FFI of its
+ * own: its hot path is the Python call surface of the third-party package
+ * `stein_thinning` (reference: code/src/thinning.py:5,17; code/src/utils/ksd.py:5-6,25,27).
+ * This header is therefore the boundary a maintainer binds with ctypes
+ * (INTEGRATION.md shows the stub).  Each entry point names the reference
+ * function whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types in any signature
+ *   - every data pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter is documented as "host"; the library allocates nothing that
+ *     outlives a call except the communicator created by gfk_comm_init
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - calls are stream-ordered and asynchronous unless documented otherwise
+ *   - return value: 0 on success, a GFK_E* code otherwise; the message is in
+ *     gfk_last_error() (thread local).  The library never aborts.
+ *   - matrices are row-major (n, d), exactly the C-contiguous float64 arrays
+ *     the reference passes around
+ */
+#ifndef GFK_H_
+#define GFK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFK_VERSION 100
+
+/* error codes */
+#define GFK_OK 0
+#define GFK_EINVAL 1    /* bad argument (shape, dtype, mode, NULL pointer)        */
+#define GFK_ECUDA 2     /* a CUDA runtime call or kernel launch failed            */
+#define GFK_ENCCL 3     /* NCCL missing, failed to load, or a collective failed   */
+#define GFK_EUNSUPPORTED 4
+#define GFK_ENUMERIC 5  /* non-finite input, zero scale, zero median              */
+
+/* arithmetic of the pair kernel */
+#define GFK_F64_STRICT 0 /* float64, numpy's operation order, no FMA contraction, correctly
+                            rounded powers: index-exact parity mode                        */
+#define GFK_F64_FAST 1   /* float64, FMA + rsqrt formulation (KSD within 1e-10 relative)   */
+#define GFK_F32_FAST 2   /* float32 pair kernel, float64 running objective (1e-5 relative) */
+
+/* Device-resident description of one thinning / KSD problem.  `x` and `s` are the
+ * STANDARDISED sample and score (gfk_standardize output), `lw` the log-weights
+ * log q - log p (NULL selects the score-based kernel k_P, non-NULL the gradient-free
+ * kernel k_PQ = exp(lw_i + lw_j) * k_Q).  For GFK_F32_FAST x/s/lw are float, else double.
+ * Scalar preconditioner Gamma^-1 = lambda * I (the only kind the reference uses);
+ * `xl` != NULL selects a dense symmetric Gamma^-1 = L: xl = x @ L (n, d) and `trace` = tr(L). */
+typedef struct gfk_problem {
+    const void* x;
+    const void* s;
+    const void* lw;   /* log-weights log q - log p (n), or NULL                             */
+    const void* w;    /* optional exp(lw) (n) for the fast modes; NULL: exp(lw_i + lw_j) per pair */
+    const void* xl;   /* optional x @ L (n, d) for a dense symmetric Gamma^-1 = L, or NULL       */
+    int64_t n;        /* rows in x / s / lw (the full replica)                          */
+    int32_t d;        /* columns                                                        */
+    int32_t mode;     /* GFK_F64_STRICT | GFK_F64_FAST | GFK_F32_FAST                   */
+    double lambda;    /* Gamma^-1 = lambda * I                                          */
+    double lambda_sq; /* (Gamma^-1 Gamma^-1)[0][0] as numpy computes it (np.dot(linv, linv)) */
+    double trace;     /* np.trace(linv), computed on the host                           */
+    double c;         /* IMQ constant c (reference: 1.0).  beta is fixed at -1/2.       */
+} gfk_problem;
+
+int gfk_version(void);
+const char* gfk_last_error(void);
+/* compute capability (major*10+minor), SM count and name of the current device; host outputs */
+int gfk_device_info(int* cc, int* sm_count, char* name, int name_len);
+
+/* ---- a3: stein_thinning.thinning._validate_and_standardize ------------------------
+ * loc = mean(x), scl = mean(|x - loc|) per column; x_out = x / scl, g_out = g * scl.
+ * With standardize = 0 the data are copied unchanged (scl = 1).  Also counts
+ * non-finite entries of x and g.  Reduction order: fixed 2048-row chunks, then the
+ * chunk partials in index order - deterministic and independent of the GPU count, but
+ * not numpy's strictly sequential order ("standardisation").
+ * SYNCHRONOUS: scl_host (d doubles, host) is valid on return.  Returns GFK_ENUMERIC if
+ * any input is non-finite or (standardize and min(scl) == 0).
+ * ws: device scratch of gfk_standardize_ws_bytes(n, d) bytes. */
+size_t gfk_standardize_ws_bytes(int64_t n, int32_t d);
+int gfk_standardize(const double* x, const double* g, int64_t n, int32_t d, int standardize,
+                    double* x_out, double* g_out, double* scl_host, void* ws, void* stream);
+
+/* ---- a2: stein_thinning.kernel.make_precon, 'med' / 'sclmed' -----------------------
+ * Median of the pairwise Euclidean distances (scipy pdist order of operations) of the
+ * rows x[linspace(0, n-1, cap, dtype=int)] if n > cap else all rows.  Writes the two
+ * middle order statistics to mid_host[2] (host; equal when the count is odd), so the
+ * caller finishes np.median / **2 / inv on the host exactly as numpy does.
+ * SYNCHRONOUS.  ws: device scratch of gfk_median_ws_bytes(n, cap) bytes. */
+size_t gfk_median_ws_bytes(int64_t n, int32_t cap);
+int gfk_median_pdist(const double* x, int64_t n, int32_t d, int32_t cap, double* mid_host,
+                     void* ws, void* stream);
+
+/* float64 -> float32 copy of a device array (count elements), for GFK_F32_FAST */
+int gfk_to_f32(const double* src, float* dst, int64_t count, void* stream);
+
+/* ---- a4: the log-weights of stein_thinning.thinning._make_stein_gf_integrand ----------
+ * lw = log_q - log_p; with use_cap: lw = max(lw - max(lw), -range_cap) (PARITY UNPINNED, see
+ * oracle/stein_thinning_oracle/thinning.py).  spread_host <- max(lw) - min(lw) of the raw
+ * difference (the caller warns when it exceeds WEIGHT_SCALE_THRESHOLD = 10, as the reference
+ * does: Gaussian_mixture.ipynb#c62).  GFK_ENUMERIC if a log-density is NaN.  SYNCHRONOUS.
+ * gfk_exp_weights: w = exp(lw) for the fast modes (is_f32: float in / float out). */
+size_t gfk_log_weights_ws_bytes(void);
+int gfk_log_weights(const double* log_p, const double* log_q, int64_t n, int use_cap, double range_cap,
+                    double* lw, double* spread_host, void* ws, void* stream);
+int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f32, void* stream);
+
+/* ---- a5 + a4: stein_thinning.thinning._greedy_search over the fused integrand -------
+ * Greedy selection of m indices (with replacement, first-index tie-break = np.argmin):
+ *   A_i = k(i, i);  idx[0] = argmin A;  repeat  A_i += 2 k(i, idx[t-1]);  idx[t] = argmin A.
+ * This rank owns candidate rows [row_begin, row_end) of the replica described by `p`
+ * (row_begin = 0, row_end = n on one GPU).  With a communicator (gfk_comm_init) the ranks
+ * exchange their (value, index) pair every step; all ranks return the same idx.
+ *   objective : device, (row_end - row_begin) doubles, the running objective A (out)
+ *   idx_out   : device, m uint32 (global row indices)
+ *   ws        : device scratch of gfk_thin_ws_bytes() bytes
+ * Asynchronous on `stream`. */
+size_t gfk_thin_ws_bytes(void);
+int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end, int32_t m,
+             double* objective, uint32_t* idx_out, void* ws, void* stream);
+
+/* ---- a7: stein_thinning.stein.ksd / kmat ----------------------------------------------
+ * gfk_ksd_rowsums: for the rows sel[0..m) of the replica (sel == NULL: rows 0..m-1),
+ *   low[t] = sum_{b<t} k(sel[t], sel[b]),  diag[t] = k(sel[t], sel[t]).
+ * Only the row tiles t with (t / 64) % n_parts == part are computed (others are written
+ * as 0), so ranks can split the triangle and all-reduce the two vectors.
+ * gfk_ksd_finish: ks[t] = sqrt(sum_{u<=t} (2 low[u] + diag[u])) / (t + 1)   (cumulative KSD).
+ * gfk_kmat: dense symmetric m x m Gram matrix (row-major, device). */
+int gfk_ksd_rowsums(const gfk_problem* p, const uint32_t* sel, int64_t m, int32_t part,
+                    int32_t n_parts, double* low, double* diag, void* stream);
+int gfk_ksd_finish(const double* low, const double* diag, int64_t m, double* ks, void* stream);
+int gfk_kmat(const gfk_problem* p, const uint32_t* sel, int64_t m, double* out, void* stream);
+/* element-wise paired kernel, the integrand protocol: out[t] = k(ia[t], ib[t]), count pairs */
+int gfk_pairs(const gfk_problem* p, const int64_t* ia, const int64_t* ib, int64_t count,
+              double* out, void* stream);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink -----------------------------------
+ * gfk_comm_unique_id: host, fills 128 bytes (ncclUniqueId) - call on rank 0, broadcast out of band.
+ * gfk_comm_init: collective; afterwards gfk_thin exchanges candidates and gfk_allreduce_sum works.
+ * nccl_path: path of libnccl.so.2 to dlopen, or NULL to use the one already loaded / default. */
+int gfk_comm_unique_id(void* id128_host, const char* nccl_path);
+int gfk_comm_init(int n_ranks, int rank, const void* id128_host, const char* nccl_path);
+int gfk_comm_size(void);
+int gfk_comm_rank(void);
+int gfk_allreduce_sum(double* buf, int64_t count, void* stream);
+int gfk_comm_finalize(void);
+
+/* ---- measurement helpers (bench.py) -----------------------------------------------------
+ * gfk_fp64_fma_peak: runs a register-resident DFMA (is_f32: FFMA) chain on every SM and
+ * writes the achieved TFLOP/s (FMA = 2 flops) to tflops_host.  SYNCHRONOUS. */
+int gfk_fma_peak(int is_f32, double* tflops_host, void* stream);
+/* writes `bytes` of device scratch to evict L2 between timed iterations */
+int gfk_flush_l2(void* scratch, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFK_H_ */

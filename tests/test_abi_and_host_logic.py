@@ -1,0 +1,94 @@
+"""CPU checks of the boundary: the C-ABI library loads and exports every symbol include/gfk.h
+declares, the product fails loudly without a GPU, the integrand protocol (code/tests/test_ksd.py)
+works for foreign callables, and the synthetic generators reproduce the reference fixture."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from gradient_free_mcmc_postprocessing_b200 import _lib, synthetic
+from gradient_free_mcmc_postprocessing_b200.stein import kmat, ksd
+from gradient_free_mcmc_postprocessing_b200.thinning import _greedy_search, thin
+from gradient_free_mcmc_postprocessing_b200.utils.ksd import reindex_integrand
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'gfk.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(gfk_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f'{name} declared in include/gfk.h but not exported'
+    assert set(names) == set(_lib.PROTOTYPES), set(names) ^ set(_lib.PROTOTYPES)
+    assert lib.gfk_version() == 100
+    assert lib.gfk_thin_ws_bytes() > 0 and lib.gfk_standardize_ws_bytes(10 ** 6, 4) > 0
+    assert lib.gfk_comm_size() == 1 and lib.gfk_comm_rank() == 0
+
+
+def test_problem_struct_layout_matches_header():
+    # 5 pointers, int64, 2 x int32, 4 doubles
+    assert ctypes.sizeof(_lib.Problem) == 5 * 8 + 8 + 4 + 4 + 4 * 8
+
+
+def test_argument_errors_without_gpu():
+    lib = _lib.load()
+    rc = lib.gfk_thin(None, 0, 0, 1, None, None, None, None)
+    assert rc == _lib.GFK_EINVAL and b'NULL' in lib.gfk_last_error()
+    with pytest.raises(ValueError):
+        _lib.mode_code('f16')
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_product_fails_loudly_without_gpu(g13):
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        thin(g13['sample'], g13['gradient'], 5)
+
+
+def test_reference_test_ksd_through_product_protocol(ref_test_ksd):
+    # port of code/tests/test_ksd.py:8-28: a foreign integrand driven through kmat + reindex_integrand
+    mat = ref_test_ksd['mat']
+    new_integrand = reindex_integrand(lambda a, b: mat[a, b], ref_test_ksd['indices'])
+    np.testing.assert_array_equal(kmat(new_integrand, mat.shape[0]), ref_test_ksd['expected'])
+
+
+def test_foreign_callable_greedy_and_ksd():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((40, 40))
+    gram = a @ a.T
+    integrand = lambda i, j: gram[i, j] if not isinstance(i, slice) else np.diag(gram)  # noqa: E731
+    idx = _greedy_search(7, lambda i, j: (np.diag(gram) if isinstance(j, slice) else gram[:, j[0]]))
+    running = np.diag(gram).copy()
+    expect = [int(np.argmin(running))]
+    for _ in range(6):
+        running += 2 * gram[:, expect[-1]]
+        expect.append(int(np.argmin(running)))
+    assert idx.dtype == np.uint32 and list(idx) == expect
+    ks = ksd(lambda i, j: gram[np.asarray(i), np.asarray(j)], 12)
+    assert np.allclose(ks, [np.sqrt(gram[:t + 1, :t + 1].sum()) / (t + 1) for t in range(12)])
+    del integrand
+
+
+def test_synthetic_generator_reproduces_reference_sample(g45):
+    rvs, logpdf, score = synthetic.make_mvn_mixture(synthetic.C1_WEIGHTS, synthetic.C1_MEANS, synthetic.C1_COVS)
+    sample = rvs(1000, np.random.default_rng(12345))
+    assert np.array_equal(sample, g45['sample'])
+    assert np.allclose(logpdf(sample), g45['log_p'], rtol=0, atol=1e-12)
+    assert np.allclose(score(sample), g45['gradient'], rtol=0, atol=1e-11)
+
+
+def test_synthetic_configs_shapes():
+    c1 = synthetic.config_c1()
+    assert c1['sample'].shape == (10_000, 2) and c1['m'] == 100
+    c2 = synthetic.config_c2(n=5000)
+    assert c2['sample'].shape == (5000, 4)
+    assert len(np.unique(c2['sample'], axis=0)) < 2500           # MCMC-like duplicated rows
