@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py - Stein-kernel pair evaluations / s for greedy gradient-free thinning on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
+                    [--precision f64|f64-fast|f32]
+
+One "step" is one complete thinning job (n candidates -> m selections): standardisation, median
+preconditioner, log-weights and the m-step greedy loop.  Workload at N = 1: BASELINE.json config C3
+(synthetic d=4 Gaussian mixture, n = 10^6, m = 1000, gradient-free kernel, 'med' preconditioner) -
+the configuration the north-star target is quoted on.  At N > 1 (one process per GPU, torchrun) the
+candidate rows are sharded across ranks and the ranks exchange one (value, index) pair per greedy
+step over NCCL; default scaling is weak (10^6 candidate rows per GPU), `--scaling strong` keeps
+n = 10^6 in total (the literal C3-on-8-GPUs case, also reported under "strong" in the weak line).
+
+`value`   : pair-evals/s with the raw inputs already resident in HBM (public API, CUDA tensors in)
+`e2e`     : the same call with pinned HOST tensors in and the numpy index vector out (H2D + D2H timed)
+`roofline`: thin_step kernel - algorithmic bytes (16d + 16 + 8 per candidate row per launch,
+            SURVEY.md section 8d) / average launch duration measured with CUDA events around the
+            launches of one job, against the measured HBM peak in MEASURED_PEAKS.json
+`cpu_baseline`: the numpy oracle (restatement of the reference's stein_thinning path) timed on this
+            host on a bounded sample of the same workload (same n, reduced m)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D, M, N_PER_GPU = 4, 1000, 1_000_000
+ALGO_BYTES_PER_ROW = {'f64': 16 * D + 16 + 8, 'f64-fast': 16 * D + 16 + 8, 'f32': 8 * D + 16 + 4}
+ALGO_FLOPS_PER_PAIR = 8 * D + 16 + 3
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--precision', default=os.environ.get('GFK_PRECISION', 'f64'),
+                    choices=['f64', 'f64-fast', 'f32'])
+    ap.add_argument('--cpu-baseline-m', type=int, default=40)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def make_inputs(n, seed=12345):
+    from gradient_free_mcmc_postprocessing_b200 import synthetic
+    c = synthetic.config_c3(n=n, d=D, seed=seed, m=M)
+    return {k: np.ascontiguousarray(c[k]) for k in ('sample', 'log_p', 'log_q', 'gradient_q')}
+
+
+# ---- reference arm: the numpy oracle on the host cores ----------------------------------------------
+_SHARED_INPUTS = None      # set before fork so the workers inherit the arrays without pickling
+
+
+def _oracle_job(args):
+    inputs, m = args
+    if inputs is None:
+        inputs = _SHARED_INPUTS
+    from oracle.stein_thinning_oracle.thinning import thin_gf
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        t0 = time.perf_counter()
+        thin_gf(inputs['sample'], inputs['log_p'], inputs['log_q'], inputs['gradient_q'], m, preconditioner='med')
+        return time.perf_counter() - t0
+
+
+def cpu_oracle_throughput(inputs, m, workers):
+    """pair-evals/s of `workers` concurrent oracle jobs (the reference parallelises across chains only,
+    code/src/utils/parallel.py:48-52; one job is single-threaded numpy)."""
+    n = inputs['sample'].shape[0]
+    if workers <= 1:
+        dt = _oracle_job((inputs, m))
+        return n * m / dt, dt
+    import multiprocessing as mp
+    global _SHARED_INPUTS
+    _SHARED_INPUTS = inputs
+    ctx = mp.get_context('fork')
+    with ctx.Pool(workers) as pool:
+        pool.map(_oracle_job, [(None, 1)] * workers)          # start the workers outside the timed region
+        t0 = time.perf_counter()
+        pool.map(_oracle_job, [(None, m)] * workers, chunksize=1)
+        dt = time.perf_counter() - t0
+    return workers * n * m / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    inputs = make_inputs(N_PER_GPU)
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    m_sample = 20
+    def one_step():
+        # the path itself is single-threaded numpy; the only parallelism the reference has is across
+        # independent chains, so time both and keep whichever uses the host better
+        single = cpu_oracle_throughput(inputs, m_sample, 1)[0]
+        multi = cpu_oracle_throughput(inputs, m_sample, workers)[0] if workers > 1 else 0.0
+        return (single, 1) if single >= multi else (multi, workers)
+
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    results = [one_step() for _ in range(args.steps)]
+    total = time.perf_counter() - t0
+    value = float(np.mean([v for v, _ in results]))
+    used = int(np.median([w for _, w in results]))
+    sample = (f'best of 1 job and {workers} concurrent single-threaded numpy jobs (the reference parallelises '
+              f'across chains only; best used {used} core(s)), each n={N_PER_GPU} d={D} GF med, '
+              f'm={m_sample} of {M} greedy steps per step')
+    workers = used
+    line = {
+        'impl': 'reference', 'metric': 'stein_kernel_pair_evals_per_s', 'value': value, 'unit': 'pair-evals/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'C3 gradient-free thinning n={N_PER_GPU} d={D} m={M} med (numpy oracle port of '
+                               'stein_thinning; bounded sample, throughput is m-independent)', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'pair-evals/s', 'cores': workers, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'pair-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
+
+
+# ---- our arm ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gradient_free_mcmc_postprocessing_b200 import _lib, distributed as gdist
+    from gradient_free_mcmc_postprocessing_b200._engine import SteinProblem
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    lib = _lib.load()
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        gdist.init()
+    warnings.simplefilter('ignore')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_case(n_total):
+        """identical replica on every rank: rank 0 generates, NCCL broadcasts; pinned host copies for e2e"""
+        names = ('sample', 'log_p', 'log_q', 'gradient_q')
+        shapes = {'sample': (n_total, D), 'log_p': (n_total,), 'log_q': (n_total,), 'gradient_q': (n_total, D)}
+        devt = {}
+        host_np = make_inputs(n_total) if rank == 0 else None
+        for k in names:
+            t = torch.from_numpy(host_np[k]).to(dev) if rank == 0 else torch.empty(shapes[k], dtype=torch.float64,
+                                                                                     device=dev)
+            if world > 1:
+                dist.broadcast(t, src=0)
+            devt[k] = t
+        pinned = {k: devt[k].cpu().pin_memory() for k in names}
+        return devt, pinned, host_np
+
+    def job(inp, timing=None):
+        prob = SteinProblem(inp['sample'], inp['gradient_q'], log_p=inp['log_p'], log_q=inp['log_q'],
+                            preconditioner='med', precision=args.precision, device=dev)
+        return prob.thin(M, timing=timing)
+
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        _lib.check(lib.gfk_flush_l2(flush_buf.data_ptr(), flush_buf.numel(), torch.cuda.current_stream().cuda_stream))
+
+    def timed_steps(inp, steps, collect_loop=False):
+        """sum of per-step CUDA-event times (L2 flushed between steps, outside the brackets); max over ranks"""
+        total_ms, loop_ms, idx = 0.0, [], None
+        for _ in range(steps):
+            flush_l2()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            timing = {} if collect_loop else None
+            e0.record()
+            idx = job(inp, timing)
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            if collect_loop:
+                loop_ms.append(timing['loop_ms'])
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), loop_ms, idx
+
+    def measure(n_total, steps, warmup):
+        devt, pinned, host_np = make_case(n_total)
+        for _ in range(warmup):
+            job(devt)
+            job(pinned)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        lib.gfk_launch_count(1)
+        dev_ms, loop_ms, idx_dev = timed_steps(devt, steps, collect_loop=True)
+        launches = lib.gfk_launch_count(1)
+        e2e_ms, _, idx_host = timed_steps(pinned, steps)
+        clocks = sampler.result()
+        assert np.array_equal(idx_dev, idx_host)
+        return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, loop_ms=loop_ms, launches=launches, clocks=clocks, idx=idx_dev,
+                    host_np=host_np, n_total=n_total)
+
+    n_total = N_PER_GPU * world if args.scaling == 'weak' else N_PER_GPU
+    res = measure(n_total, args.steps, args.warmup)
+    strong = None
+    if world > 1 and args.scaling == 'weak':
+        strong = measure(N_PER_GPU, max(2, args.steps // 2), 2)
+
+    # measured FP64 FMA peak (not in MEASURED_PEAKS.json)
+    import ctypes
+    fp64 = ctypes.c_double()
+    _lib.check(lib.gfk_fma_peak(0, ctypes.byref(fp64), None))
+
+    if rank == 0:
+        pairs = float(n_total) * M
+        ms_per_step = res['dev_ms'] / args.steps
+        value = pairs / (ms_per_step * 1e-3)
+        e2e_ms_per_step = res['e2e_ms'] / args.steps
+        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(peaks_path):
+            peak_gbs, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        else:
+            peak_gbs, peak_src = FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
+        rows_local = -(-n_total // world)
+        launch_ms = float(np.mean(res['loop_ms'])) / M          # m launches of ~equal cost: init + (m-1) steps
+        algo_bytes = ALGO_BYTES_PER_ROW[args.precision] * rows_local
+        achieved = algo_bytes / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f'thin_step:{args.precision}:bytes_per_launch')
+        h2d = sum(int(np.prod(s)) * 8 for s in ((n_total, D), (n_total, D), (n_total,), (n_total,)))
+        line = {
+            'metric': 'stein_kernel_pair_evals_per_s', 'value': value, 'unit': 'pair-evals/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64' if args.precision != 'f32' else 'f32',
+            'data': 'synthetic',
+            'config': {'workload': f'C3 gradient-free Stein thinning: d={D} Gaussian mixture, n={n_total} '
+                                   f'({rows_local} candidate rows per GPU), m={M}, preconditioner=med, '
+                                   f'precision={args.precision}',
+                       'thinning_wall_time_ms': ms_per_step, 'l2': 'flushed between timed steps (512 MiB write)',
+                       'step': 'one full thinning job n->m (standardise + median + log-weights + m greedy steps)'},
+            'e2e': {'value': pairs / (e2e_ms_per_step * 1e-3), 'unit': 'pair-evals/s', 'ms_per_step': e2e_ms_per_step,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * M},
+            'gpu_launches': int(res['launches']),
+            'clocks': res['clocks'],
+            'roofline': {'bound': 'hbm', 'kernel': 'thin_step_small_kernel', 'achieved': achieved, 'peak': peak_gbs,
+                         'unit': 'GB/s', 'frac': achieved / peak_gbs, 'traffic': traffic, 'peak_source': peak_src,
+                         'launch_us': launch_ms * 1e3, 'algorithmic_bytes_per_launch': algo_bytes,
+                         'alu': {'fp64_fma_peak_tflops_measured': fp64.value,
+                                 'achieved_tflops': ALGO_FLOPS_PER_PAIR * rows_local / (launch_ms * 1e-3) / 1e12,
+                                 'flops_per_pair': ALGO_FLOPS_PER_PAIR}},
+        }
+        if strong is not None:
+            sm = strong['dev_ms'] / max(2, args.steps // 2)
+            line['strong'] = {'n': N_PER_GPU, 'ms_per_step': sm, 'value': N_PER_GPU * M / (sm * 1e-3),
+                              'e2e_ms_per_step': strong['e2e_ms'] / max(2, args.steps // 2)}
+        if world == 1 and not args.no_cpu_baseline:
+            m_cpu = args.cpu_baseline_m
+            v, dt = cpu_oracle_throughput(res['host_np'], m_cpu, 1)
+            from oracle.stein_thinning_oracle.thinning import thin_gf as oracle_thin_gf  # checker
+            line['cpu_baseline'] = {'value': v, 'unit': 'pair-evals/s', 'cores': 1, 'kind': 'port',
+                                    'host_cores_available': os.cpu_count(), 'seconds': dt,
+                                    'sample': f'numpy oracle thin_gf on the same n={n_total} d={D} inputs, first '
+                                              f'{m_cpu} of {M} greedy steps (throughput is m-independent)'}
+            h = res['host_np']
+            expect = oracle_thin_gf(h['sample'], h['log_p'], h['log_q'], h['gradient_q'], 8, preconditioner='med')
+            line['parity_prefix_ok'] = bool(np.array_equal(expect, res['idx'][:8]))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
+        gdist.finalize()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

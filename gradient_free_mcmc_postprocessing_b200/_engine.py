@@ -212,8 +212,9 @@ class SteinProblem:
                               trace=self.trace, c=self.c)
 
     # -- operations -------------------------------------------------------------------------------
-    def thin(self, n_points, row_range=None, return_objective=False):
-        """``_greedy_search`` over this problem; returns ``np.ndarray`` of ``uint32`` (length n_points)."""
+    def thin(self, n_points, row_range=None, return_objective=False, timing=None):
+        """``_greedy_search`` over this problem; returns ``np.ndarray`` of ``uint32`` (length n_points).
+        ``timing`` (dict, optional) receives ``loop_ms``: CUDA-event time of the gfk_thin launches alone."""
         lib = _lib.load()
         m = int(n_points)
         if m < 1:
@@ -226,9 +227,17 @@ class SteinProblem:
             objective = torch.empty(r1 - r0, dtype=torch.float64, device=self.device)
             idx = torch.empty(m, dtype=torch.int32, device=self.device)
             ws = _bytes(lib.gfk_thin_ws_bytes(), self.device)
+            if timing is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             check(lib.gfk_thin(ctypes.byref(self.struct), r0, r1, m, _ptr(objective), _ptr(idx), _ptr(ws),
                                _stream_ptr(self.device)))
+            if timing is not None:
+                e1.record()
             out = idx.cpu().numpy().view(np.uint32)
+            if timing is not None:
+                timing['loop_ms'] = e0.elapsed_time(e1)
+                timing['rows'] = r1 - r0
         if return_objective:
             return out, objective
         return out

@@ -40,6 +40,7 @@ _pp = ctypes.POINTER(Problem)
 _pd = ctypes.POINTER(ctypes.c_double)
 PROTOTYPES = {
     'gfk_version': (ctypes.c_int, []),
+    'gfk_launch_count': (ctypes.c_longlong, [ctypes.c_int]),
     'gfk_last_error': (ctypes.c_char_p, []),
     'gfk_device_info': (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                        ctypes.c_char_p, ctypes.c_int]),

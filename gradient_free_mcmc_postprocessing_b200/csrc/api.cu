@@ -1,5 +1,7 @@
 // api.cu - error plumbing, device queries and the measurement helpers of libgfk.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -19,6 +21,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
     return GFK_ECUDA;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -60,6 +65,11 @@ __global__ void flush_kernel(uint4* p, size_t count) {
 using namespace gfk;
 
 extern "C" int gfk_version(void) { return GFK_VERSION; }
+extern "C" long long gfk_launch_count(int reset) {
+    const long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
 extern "C" const char* gfk_last_error(void) { return g_err; }
 
 extern "C" int gfk_device_info(int* cc, int* sms, char* name, int name_len) {
@@ -97,6 +107,7 @@ extern "C" int gfk_fma_peak(int is_f32, double* tflops_host, void* stream) {
         GFK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0 && ms < best_ms) best_ms = ms;
     }
+    count_launches(6);
     const double flops = 2.0 * 16.0 * (double)iters * (double)grid * threads;
     *tflops_host = flops / (best_ms * 1e-3) / 1e12;
     cudaEventDestroy(e0);
@@ -110,6 +121,7 @@ extern "C" int gfk_flush_l2(void* scratch, size_t bytes, void* stream) {
     GFK_REQUIRE(scratch && bytes >= 16, "gfk_flush_l2: bad arguments");
     flush_kernel<<<sm_count() * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(scratch),
                                                                                bytes / 16);
+    count_launches(1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }

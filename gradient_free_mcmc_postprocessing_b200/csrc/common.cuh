@@ -31,6 +31,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 
 int sm_count();
+// running count of kernel launches issued by this library (gfk_launch_count)
+void count_launches(long long n);
 
 // ---- warp / block argmin with numpy.argmin semantics -----------------------------------------
 __device__ __forceinline__ void warp_argmin(double& v, unsigned& i) {

@@ -342,6 +342,7 @@ static int rowsums_typed(const gfk_problem* p, const uint32_t* sel, int64_t m, i
             ksd_rowsum_kernel<T, false, KC><<<(unsigned)my_tiles, KSD_THREADS, smem, st>>>(a);
         }
     }
+    count_launches(my_tiles > 0 ? 2 : 1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }
@@ -375,6 +376,7 @@ extern "C" int gfk_ksd_rowsums(const gfk_problem* p, const uint32_t* sel, int64_
 extern "C" int gfk_ksd_finish(const double* low, const double* diag, int64_t m, double* ks, void* stream) {
     GFK_REQUIRE(low && diag && ks && m >= 1, "gfk_ksd_finish: bad arguments");
     ksd_finish_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(low, diag, m, ks);
+    count_launches(1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }
@@ -389,6 +391,7 @@ extern "C" int gfk_kmat(const gfk_problem* p, const uint32_t* sel, int64_t m, do
     if (p->mode == GFK_F64_STRICT) kmat_kernel<double, true><<<g, 256, 0, st>>>(make_args<double>(p, sel, m), out);
     else if (p->mode == GFK_F64_FAST) kmat_kernel<double, false><<<g, 256, 0, st>>>(make_args<double>(p, sel, m), out);
     else kmat_kernel<float, false><<<g, 256, 0, st>>>(make_args<float>(p, sel, m), out);
+    count_launches(1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }
@@ -409,6 +412,7 @@ extern "C" int gfk_pairs(const gfk_problem* p, const int64_t* ia, const int64_t*
         pairs_kernel<double, false><<<g, 256, 0, st>>>(make_args<double>(p, nullptr, 0), a64, b64, count, out);
     else
         pairs_kernel<float, false><<<g, 256, 0, st>>>(make_args<float>(p, nullptr, 0), a64, b64, count, out);
+    count_launches(1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }

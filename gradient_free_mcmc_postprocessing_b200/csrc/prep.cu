@@ -242,6 +242,7 @@ extern "C" int gfk_standardize(const double* x, const double* g, int64_t n, int3
         col_finish_kernel<<<1, 128, 0, st>>>(partial, nchunks, d, n, scl);
     }
     scale_kernel<<<grid_for(n * d, 256), 256, 0, st>>>(x, g, n * d, d, scl, standardize, x_out, g_out, nonfinite);
+    count_launches(standardize ? 5 : 3);
     GFK_CHECK_LAUNCH();
     unsigned long long bad = 0;
     GFK_CUDA(cudaMemcpyAsync(&bad, nonfinite, sizeof(bad), cudaMemcpyDeviceToHost, st));
@@ -296,6 +297,7 @@ extern "C" int gfk_median_pdist(const double* x, int64_t n, int32_t d, int32_t c
     const long long k1 = npairs / 2;
     const long long k0 = (npairs % 2 == 0) ? k1 - 1 : k1;
     radix_select_kernel<<<2, 1024, 0, st>>>(dist, npairs, k0, k1, out2);
+    count_launches(2);
     GFK_CHECK_LAUNCH();
     GFK_CUDA(cudaMemcpyAsync(mid_host, out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     GFK_CUDA(cudaStreamSynchronize(st));  // also keeps `rows` alive until the copy has been consumed
@@ -306,6 +308,7 @@ extern "C" int gfk_to_f32(const double* src, float* dst, int64_t count, void* st
     GFK_REQUIRE(src && dst && count >= 0, "gfk_to_f32: bad arguments");
     if (count == 0) return GFK_OK;
     to_f32_kernel<<<grid_for(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, count);
+    count_launches(1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }
@@ -320,6 +323,7 @@ extern "C" int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f3
     else
         exp_weights_kernel<double><<<grid_for(count, 256), 256, 0, st>>>(static_cast<const double*>(lw),
                                                                          static_cast<double*>(w), count);
+    count_launches(1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }
@@ -350,6 +354,7 @@ extern "C" int gfk_log_weights(const double* log_p, const double* log_q, int64_t
     }
     *spread_host = mx - mn;
     lw_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(log_p, log_q, n, use_cap, mx, range_cap, lw);
+    count_launches(2);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }

@@ -44,23 +44,42 @@ struct ThinArgs {
 };
 
 // ---- row access -------------------------------------------------------------------------------
-template <typename T, int D>
-__device__ __forceinline__ void load_row(const T* __restrict__ base, long long row, T (&out)[D]) {
-    constexpr int bytes = D * (int)sizeof(T);
-    const T* p = base + row * D;
-    if constexpr (bytes % 16 == 0) {
-        const uint4* q = reinterpret_cast<const uint4*>(p);
+// One row of D values with the widest aligned vector loads the row size allows (rows of a
+// torch allocation start 16-byte aligned whenever D * sizeof(T) is a multiple of 16).
+template <int D>
+__device__ __forceinline__ void load_row(const double* __restrict__ base, long long row, double (&out)[D]) {
+    const double* p = base + row * D;
+    if constexpr (D % 2 == 0) {
+        const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
-        for (int v = 0; v < bytes / 16; ++v) {
-            const uint4 u = __ldg(q + v);
-            *reinterpret_cast<uint4*>(&out[v * (16 / sizeof(T))]) = u;
+        for (int v = 0; v < D / 2; ++v) {
+            const double2 u = __ldg(q + v);
+            out[2 * v] = u.x;
+            out[2 * v + 1] = u.y;
         }
-    } else if constexpr (bytes % 8 == 0) {
-        const uint2* q = reinterpret_cast<const uint2*>(p);
+    } else {
 #pragma unroll
-        for (int v = 0; v < bytes / 8; ++v) {
-            const uint2 u = __ldg(q + v);
-            *reinterpret_cast<uint2*>(&out[v * (8 / sizeof(T))]) = u;
+        for (int k = 0; k < D; ++k) out[k] = __ldg(p + k);
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void load_row(const float* __restrict__ base, long long row, float (&out)[D]) {
+    const float* p = base + row * D;
+    if constexpr (D % 4 == 0) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int v = 0; v < D / 4; ++v) {
+            const float4 u = __ldg(q + v);
+            out[4 * v] = u.x; out[4 * v + 1] = u.y; out[4 * v + 2] = u.z; out[4 * v + 3] = u.w;
+        }
+    } else if constexpr (D % 2 == 0) {
+        const float2* q = reinterpret_cast<const float2*>(p);
+#pragma unroll
+        for (int v = 0; v < D / 2; ++v) {
+            const float2 u = __ldg(q + v);
+            out[2 * v] = u.x;
+            out[2 * v + 1] = u.y;
         }
     } else {
 #pragma unroll
@@ -171,8 +190,8 @@ __global__ void __launch_bounds__(kThreads) thin_step_small_kernel(ThinArgs<T> a
         a.ws->step += 1;
     }
     T y[D], sy[D];
-    load_row<T, D>(a.x, sel, y);
-    load_row<T, D>(a.s, sel, sy);
+    load_row<D>(a.x, sel, y);
+    load_row<D>(a.s, sel, sy);
     T lwy = T(0), wy = T(0);
     if (a.lw) {
         lwy = __ldg(a.lw + sel);
@@ -191,8 +210,8 @@ __global__ void __launch_bounds__(kThreads) thin_step_small_kernel(ThinArgs<T> a
             const long long li = base + j * kThreads + threadIdx.x;
             if (li < rows) {
                 const long long i = a.row_begin + li;
-                load_row<T, D>(a.x, i, xr[j]);
-                load_row<T, D>(a.s, i, sr[j]);
+                load_row<D>(a.x, i, xr[j]);
+                load_row<D>(a.s, i, sr[j]);
                 av[j] = a.A[li];
                 wt[j] = a.lw ? weight_pair<T, STRICT>(a, i, lwy, wy) : 1.0;
             }
@@ -401,6 +420,7 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
         launch_step<T, STRICT>(a, d, st, grid_small, grid_tiled, tiled_threads, tiled_smem);
     }
     thin_finish_kernel<<<1, 32, 0, st>>>(a.ws, idx_out, a.n_ranks);
+    count_launches(2 + (long long)m);   // reset + init + (m - 1) steps + finish
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }

@@ -68,6 +68,8 @@ typedef struct gfk_problem {
 } gfk_problem;
 
 int gfk_version(void);
+/* kernel launches issued by this library so far (process-wide); reset != 0 zeroes the counter */
+long long gfk_launch_count(int reset);
 const char* gfk_last_error(void);
 /* compute capability (major*10+minor), SM count and name of the current device; host outputs */
 int gfk_device_info(int* cc, int* sm_count, char* name, int name_len);

@@ -1,0 +1,54 @@
+"""Worker for tests/test_multigpu.py: run under torchrun with >= 2 GPUs (one rank per GPU, NCCL)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from gradient_free_mcmc_postprocessing_b200 import distributed as gdist, synthetic  # noqa: E402
+from gradient_free_mcmc_postprocessing_b200.stein import ksd  # noqa: E402
+from gradient_free_mcmc_postprocessing_b200.thinning import _make_stein_gf_integrand, thin, thin_gf  # noqa: E402
+from oracle.stein_thinning_oracle import stein as os_, thinning as ot  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
+    dist.init_process_group('nccl')
+    gdist.init()
+    warnings.simplefilter('ignore')
+    # duplicated rows -> exact ties that straddle shard boundaries
+    c = synthetic.config_c2(n=30_011, m=80)
+    got = thin(c['sample'], c['gradient'], 80, preconditioner='med')
+    expect = ot.thin(c['sample'], c['gradient'], 80, preconditioner='med')
+    assert np.array_equal(got, expect), (rank, got[:10], expect[:10])
+    c1 = synthetic.config_c1()
+    got = thin_gf(c1['sample'], c1['log_p'], c1['log_q'], c1['gradient_q'], 100, preconditioner='med')
+    expect = ot.thin_gf(c1['sample'], c1['log_p'], c1['log_q'], c1['gradient_q'], 100, preconditioner='med')
+    assert np.array_equal(got, expect)
+    # every rank returns the same sequence
+    t = torch.from_numpy(got.astype(np.int64)).cuda()
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    assert all(torch.equal(g, t) for g in gathered)
+    # sharded KSD triangle + all-reduce
+    n = 3000
+    integ = _make_stein_gf_integrand(c1['sample'][:n], c1['log_p'][:n], c1['log_q'][:n], c1['gradient_q'][:n],
+                                     preconditioner='med')
+    ref = ot._make_stein_gf_integrand(c1['sample'][:n], c1['log_p'][:n], c1['log_q'][:n], c1['gradient_q'][:n],
+                                      preconditioner='med')
+    np.testing.assert_allclose(ksd(integ, n), os_.ksd(ref, n), rtol=1e-10)
+    dist.barrier()
+    gdist.finalize()
+    dist.destroy_process_group()
+    if rank == 0:
+        print('MGPU_OK world', world)
+
+
+if __name__ == '__main__':
+    main()
