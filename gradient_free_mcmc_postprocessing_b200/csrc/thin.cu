@@ -11,6 +11,8 @@
 // (algorithmic traffic 16d + 16 (+8) bytes per row in float64), adds 2 k(x_i, y) to A_i and
 // keeps a running (min, first index).  Warp shuffle -> block -> last-block-done grid reduction
 // produces the rank's candidate for the next exchange.  No host round trip inside the loop.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "comm.h"
 
@@ -24,8 +26,9 @@ struct __align__(16) ThinWs {
     Cand send;               // this rank's (value, global index)
     Cand recv[kMaxRanks];    // all ranks' candidates after the exchange
     Cand partial[kMaxBlocks];
-    unsigned counter;        // last-block-done ticket
+    unsigned counter;        // last-block-done ticket / persistent-kernel barrier arrivals
     unsigned step;           // greedy step whose winner is in recv[]
+    unsigned abort;          // persistent kernel: a barrier spin ran out (never expected)
 };
 
 template <typename T>
@@ -316,6 +319,168 @@ __global__ void thin_step_tiled_kernel(ThinArgs<T> a) {
     grid_argmin_publish(bv, bi, a.ws, a.n_ranks);
 }
 
+// ---- all m greedy steps in ONE cooperative launch (single rank, small D) -------------------------------
+// One CTA per SM (or fewer for small shards).  Thread g of the grid owns rows g, g + T, g + 2T, ... for the
+// whole job (T = threads in the grid).  The running objective A and the log-weights of the owned rows live
+// in shared memory for all m steps; if the shard is small enough the owned x / s rows are copied to shared
+// memory too (SoA, conflict-free) and the step loop touches no global memory at all except the selected
+// row - otherwise x / s are re-read each step through L2 (no HBM traffic once the 126 MB L2 holds them).
+// Per step: local update + argmin -> block argmin -> partial[parity][cta] -> grid barrier (arrival counter)
+// -> every CTA reduces the <= 148 partials itself (no second barrier) -> next selected row.
+constexpr int kPersistThreads = 512;
+constexpr unsigned kSpinLimit = 1u << 27;
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+    return *reinterpret_cast<const volatile unsigned*>(p);
+}
+
+template <typename T, int D, bool STRICT, bool RESIDENT>
+__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt) {
+    extern __shared__ __align__(16) unsigned char psm[];
+    __shared__ double sv[32];
+    __shared__ unsigned si[32];
+    __shared__ unsigned long long win_sh;
+    __shared__ int abort_sh;
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    const long long TT = (long long)gridDim.x * nthr;
+    const long long gt = (long long)blockIdx.x * nthr + tid;
+    const long long rows = a.row_end - a.row_begin;
+    const int slots = rpt * nthr;
+    double* A_sh = reinterpret_cast<double*>(psm);
+    T* lw_sh = reinterpret_cast<T*>(A_sh + slots);              // lw (strict / no w) or w (fast)
+    T* xs = lw_sh + (a.lw ? slots : 0);                          // RESIDENT: x as [D][slots], then s
+    T* ss = xs + (RESIDENT ? (size_t)D * slots : 0);
+    const bool use_w = (!STRICT && a.w != nullptr);
+    ThinWs* ws = a.ws;
+    Cand* partial0 = ws->partial;
+    Cand* partial1 = ws->partial + kMaxBlocks / 2;
+    if (tid == 0) abort_sh = 0;
+
+    // ---- step 0: diagonal, and stage the owned rows ----------------------------------------------------
+    double bv = __longlong_as_double(0x7ff0000000000000LL);
+    unsigned bi = 0xffffffffu;
+    for (int j = 0; j < rpt; ++j) {
+        const long long li = (long long)j * TT + gt;
+        const int slot = j * nthr + tid;
+        if (li < rows) {
+            const long long i = a.row_begin + li;
+            T xr[D], sr[D];
+            load_row<D>(a.x, i, xr);
+            load_row<D>(a.s, i, sr);
+            if (RESIDENT) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) { xs[k * slots + slot] = xr[k]; ss[k * slots + slot] = sr[k]; }
+            }
+            double k0;
+            if constexpr (STRICT) k0 = pair_strict<D>(xr, xr, sr, sr, a.kp);
+            else k0 = (double)pair_fast<T, D, false>(xr, xr, sr, sr, xr, xr, a.kp);
+            if (a.lw) {
+                const T lwi = __ldg(a.lw + i);
+                if (use_w) {
+                    const T wi = __ldg(a.w + i);
+                    lw_sh[slot] = wi;
+                    k0 *= (double)(wi * wi);
+                } else {
+                    lw_sh[slot] = lwi;
+                    const double wgt = exp((double)lwi + (double)lwi);
+                    k0 = STRICT ? __dmul_rn(wgt, k0) : wgt * k0;
+                }
+            }
+            A_sh[slot] = k0;
+            if (cand_better(k0, (unsigned)i, bv, bi)) { bv = k0; bi = (unsigned)i; }
+        }
+    }
+
+    for (int step = 0; step < m; ++step) {
+        // ---- grid-wide argmin of the running objective ----------------------------------------------
+        Cand* partial = (step & 1) ? partial1 : partial0;
+        block_argmin(bv, bi, sv, si);
+        if (tid == 0) {
+            partial[blockIdx.x].v = bv;
+            partial[blockIdx.x].i = bi;
+            __threadfence();
+            atomicAdd(&ws->counter, 1u);
+            const unsigned target = (unsigned)(step + 1) * gridDim.x;
+            unsigned spins = 0;
+            while (ld_volatile_u32(&ws->counter) < target) {
+                if (++spins > kSpinLimit || ld_volatile_u32(&ws->abort)) { abort_sh = 1; ws->abort = 1; break; }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (abort_sh) break;
+        if (tid < 32) {
+            double wv = __longlong_as_double(0x7ff0000000000000LL);
+            unsigned wi = 0xffffffffu;
+            for (unsigned b = tid; b < gridDim.x; b += 32) {
+                const double pv = __ldcg(&partial[b].v);
+                const unsigned pi = (unsigned)__ldcg(&partial[b].i);
+                if (cand_better(pv, pi, wv, wi)) { wv = pv; wi = pi; }
+            }
+            warp_argmin(wv, wi);
+            if (tid == 0) {
+                win_sh = wi;
+                if (blockIdx.x == 0) {
+                    a.idx_out[step] = wi;
+                    if (step == m - 1) { ws->send.v = wv; ws->send.i = wi; ws->recv[0] = ws->send; ws->step = (unsigned)m; }
+                }
+            }
+        }
+        __syncthreads();
+        if (step == m - 1) break;
+        const long long sel = (long long)win_sh;
+
+        // ---- add 2 k(x_i, y) for the new selection y ---------------------------------------------------
+        T y[D], sy[D];
+        load_row<D>(a.x, sel, y);
+        load_row<D>(a.s, sel, sy);
+        T lwy = T(0);
+        if (a.lw) lwy = use_w ? __ldg(a.w + sel) : __ldg(a.lw + sel);
+        bv = __longlong_as_double(0x7ff0000000000000LL);
+        bi = 0xffffffffu;
+#pragma unroll 2
+        for (int j = 0; j < rpt; ++j) {
+            const long long li = (long long)j * TT + gt;
+            const int slot = j * nthr + tid;
+            if (li < rows) {
+                const long long i = a.row_begin + li;
+                T xr[D], sr[D];
+                if (RESIDENT) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots + slot]; sr[k] = ss[k * slots + slot]; }
+                } else {
+                    load_row<D>(a.x, i, xr);
+                    load_row<D>(a.s, i, sr);
+                }
+                double k;
+                if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
+                else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
+                double v;
+                const double av = A_sh[slot];
+                if constexpr (STRICT) {
+                    if (a.lw) k = __dmul_rn(exp((double)lw_sh[slot] + (double)lwy), k);
+                    v = __dadd_rn(av, __dmul_rn(2.0, k));
+                } else {
+                    if (a.lw) {
+                        const double wgt = use_w ? (double)(lw_sh[slot] * lwy) : exp((double)lw_sh[slot] + (double)lwy);
+                        v = fma(2.0 * wgt, k, av);
+                    } else {
+                        v = fma(2.0, k, av);
+                    }
+                }
+                A_sh[slot] = v;
+                if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
+            }
+        }
+    }
+    // ---- write the running objective back -----------------------------------------------------------
+    for (int j = 0; j < rpt; ++j) {
+        const long long li = (long long)j * TT + gt;
+        if (li < rows) a.A[li] = A_sh[j * nthr + tid];
+    }
+}
+
 // winner of the last exchange -> idx_out[m - 1]
 __global__ void thin_finish_kernel(ThinWs* ws, uint32_t* idx_out, int n_ranks) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -329,6 +494,7 @@ __global__ void thin_reset_kernel(ThinWs* ws) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ws->counter = 0;
         ws->step = 0;
+        ws->abort = 0;
     }
 }
 
@@ -364,6 +530,66 @@ static int launch_step(const ThinArgs<T>& a, int d, cudaStream_t st, int grid_sm
         thin_step_tiled_kernel<T, STRICT><<<grid_tiled, tiled_threads, tiled_smem, st>>>(a);
     }
     return GFK_OK;
+}
+
+
+// persistent path: returns 1 if it ran, 0 if not eligible, < 0 on error
+template <typename T, int D, bool STRICT>
+static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
+    const long long rows = a.row_end - a.row_begin;
+    int dev = 0, coop = 0, smem_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (!coop) return 0;
+    const int sms = sm_count();
+    long long grid = (rows + kPersistThreads - 1) / kPersistThreads;
+    if (grid > sms) grid = sms;
+    if (grid > kMaxBlocks / 2) grid = kMaxBlocks / 2;
+    const long long TT = grid * kPersistThreads;
+    const int rpt = (int)((rows + TT - 1) / TT);
+    const size_t slots = (size_t)rpt * kPersistThreads;
+    const size_t base = slots * (sizeof(double) + (a.lw ? sizeof(T) : 0));
+    const size_t resident = base + 2 * (size_t)D * slots * sizeof(T);
+    const size_t budget = (size_t)smem_optin - 1024;   // static shared of the kernel
+    bool use_resident = resident <= budget;
+    if (base > budget) return 0;
+    const char* env = getenv("GFK_RESIDENT");
+    if (env && env[0] == '0') use_resident = false;
+    const size_t smem = use_resident ? resident : base;
+    ThinArgs<T> args = a;
+    int m_arg = m, rpt_arg = rpt;
+    void* params[] = {&args, &m_arg, &rpt_arg};
+    const void* fn = use_resident ? (const void*)thin_persistent_kernel<T, D, STRICT, true>
+                                  : (const void*)thin_persistent_kernel<T, D, STRICT, false>;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kPersistThreads, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    thin_reset_kernel<<<1, 32, 0, st>>>(a.ws);
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kPersistThreads), params, smem, st);
+    if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
+    count_launches(2);
+    return 1;
+}
+
+template <typename T, bool STRICT>
+static int try_persistent(const ThinArgs<T>& a, int d, int m, cudaStream_t st) {
+    const char* env = getenv("GFK_PERSISTENT");
+    if (env && env[0] == '0') return 0;
+    if (a.n_ranks != 1 || a.xl != nullptr) return 0;
+    switch (d) {
+        case 1: return try_persistent_d<T, 1, STRICT>(a, m, st);
+        case 2: return try_persistent_d<T, 2, STRICT>(a, m, st);
+        case 3: return try_persistent_d<T, 3, STRICT>(a, m, st);
+        case 4: return try_persistent_d<T, 4, STRICT>(a, m, st);
+        default: return 0;
+    }
 }
 
 template <typename T, bool STRICT>
@@ -403,6 +629,11 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
         if (blocks < 1) blocks = 1;
         return (int)blocks;
     };
+    {
+        const int pr = try_persistent<T, STRICT>(a, d, m, st);
+        if (pr < 0) return -pr;
+        if (pr == 1) return GFK_OK;
+    }
     const int grid_init = grid_for(kThreads, 8);
     const int grid_small = grid_for(kThreads * 2, 4);
     const int grid_tiled = uses_tiled ? grid_for(tiled_threads, tiled_smem > 50 * 1024 ? 2 : 4) : 1;

@@ -51,7 +51,13 @@ def timed(fn, reps=3):
 
 warnings.simplefilter('ignore')
 timings = {}
-for cname in ('c1', 'c2', 'c3', 'c5'):
+variants = [('persist', {}), ('persist-stream', {'GFK_RESIDENT': '0'}), ('multilaunch', {'GFK_PERSISTENT': '0'})]
+for cname, var in [(c, v) for c in ('c1', 'c2', 'c3', 'c5') for v in variants]:
+    if cname == 'c5' and var[0] != 'multilaunch':
+        continue
+    for k in ('GFK_RESIDENT', 'GFK_PERSISTENT'):
+        os.environ.pop(k, None)
+    os.environ.update(var[1])
     c = synthetic.CONFIGS[cname]()
     n, d = c['sample'].shape
     for prec in ('f64', 'f64-fast', 'f32'):
@@ -64,11 +70,14 @@ for cname in ('c1', 'c2', 'c3', 'c5'):
         torch.cuda.synchronize()
         t_setup = time.perf_counter() - t0
         t = timed(lambda: p.thin(c['m']))
-        timings[f'{cname}:{prec}'] = dict(n=n, d=d, m=c['m'], setup_s=t_setup, thin_s=t,
-                                          pair_evals_per_s=n * c['m'] / t, us_per_step=t / c['m'] * 1e6)
-        print(cname, prec, timings[f'{cname}:{prec}'], flush=True)
+        key = f'{cname}:{var[0]}:{prec}'
+        timings[key] = dict(n=n, d=d, m=c['m'], setup_s=t_setup, thin_s=t,
+                            pair_evals_per_s=n * c['m'] / t, us_per_step=t / c['m'] * 1e6)
+        print(key, timings[key], flush=True)
         del p
 out['thin'] = timings
+for k in ('GFK_RESIDENT', 'GFK_PERSISTENT'):
+    os.environ.pop(k, None)
 c = synthetic.config_c4(n=50_000)
 for prec in ('f64-fast', 'f32'):
     p = SteinProblem(c['sample'], c['gradient_q'], log_p=c['log_p'], log_q=c['log_q'], preconditioner='med',
