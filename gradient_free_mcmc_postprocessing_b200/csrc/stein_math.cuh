@@ -20,6 +20,7 @@
 #pragma once
 
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define GFK_HD __host__ __device__ __forceinline__
@@ -56,36 +57,81 @@ GFK_HD double nf_sub(double a, double b) { return a - b; }
 GFK_HD double nf_sqrt(double a) { return sqrt(a); }
 GFK_HD double nf_div(double a, double b) { return a / b; }
 GFK_HD double nf_fma(double a, double b, double c) { return fma(a, b, c); }
+#if defined(GFK_TEST_RSQRT_PERTURB)
+// test hook (tests/host): emulate a reciprocal square root that is several ulp off, as a device
+// approximation may be, to show the correction steps below do not depend on its last bits
+GFK_HD double approx_rsqrt(double a) {
+    const double r = 1.0 / sqrt(a);
+    unsigned long long bits;
+    memcpy(&bits, &a, sizeof(bits));
+    const int k = (int)((bits * 0x9E3779B97F4A7C15ull) >> 61) - 3;   // -3 .. 4 ulp
+    return r * (1.0 + k * 2.220446049250313e-16);
+}
+#else
 GFK_HD double approx_rsqrt(double a) { return 1.0 / sqrt(a); }
+#endif
 GFK_HD float approx_rsqrt(float a) { return 1.0f / sqrtf(a); }
 #endif
 
 GFK_HD double fma_t(double a, double b, double c) { return nf_fma(a, b, c); }
 GFK_HD float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 
-// q^0.5 (correctly rounded), q^1.5 and q^2.5 (correctly rounded up to ~2^-100) for q >= 0.
-// sqrt(q) = s + sl with s = RN(sqrt q), sl = (q - s*s) / (2 s); the products q * (s + sl) and
-// q^2 * (s + sl) are formed in double-double and rounded once.
-GFK_HD void strict_powers(double q, double& p05, double& p15, double& p25) {
-    const double s = nf_sqrt(q);
+// Correctly rounded quotient n / p from an approximate reciprocal rinv ~ 1/p (a few ulp): one
+// Markstein correction step.  q0 = n * rinv is within a few ulp of n / p, the residual n - q0 * p is
+// exact in an FMA, and q0 + resid * rinv is then accurate to ~2^-100 relative before its single final
+// rounding (a quotient of doubles is never closer than ~2^-106 relative to a rounding midpoint, so the
+// result equals IEEE division except in astronomically rare cases).  Falls back to IEEE division
+// outside the safe exponent range or for non-finite operands.
+GFK_HD double div_markstein(double n, double p, double rinv) {
+    const double q0 = nf_mul(n, rinv);
+    const double resid = nf_fma(-q0, p, n);
+    const double q = nf_fma(resid, rinv, q0);
+    const double an = fabs(n), ap = fabs(p);
+    const bool safe = (ap > 1.0e-140) && (ap < 1.0e140) && (an < 1.0e140) && ((an > 1.0e-140) || (n == 0.0));
+    return safe ? q : nf_div(n, p);
+}
+
+// q^0.5, q^1.5 and q^2.5, each correctly rounded up to ~2^-100 (q >= 0), plus approximate reciprocals
+// (a few ulp) of the three powers for div_markstein.
+// r = rsqrt(q) approximately; s0 = q * r; sqrt(q) = s0 + (q - s0^2) * r / 2 to ~2^-100: the rounded sum is
+// RN(sqrt q) (sqrt of a double is never closer than ~2^-105 relative to a midpoint), and the unrounded pair
+// (s, sl) feeds the double-double products q * sqrt(q) and q^2 * sqrt(q), each rounded once.
+GFK_HD void strict_powers_r(double q, double& p05, double& p15, double& p25, double& r05, double& r15,
+                            double& r25) {
+    const double r = approx_rsqrt(q);
+    const double hr = nf_mul(0.5, r);
+    const double s0 = nf_mul(q, r);
+    const double e0 = nf_fma(-s0, s0, q);                   // exact: q - s0*s0
+    double s = nf_fma(e0, hr, s0);                          // RN(sqrt q) w.h.p.
+    const bool regular = (q > 1.0e-290) && (q < 1.0e300);
+    if (!regular) s = nf_sqrt(q);
     p05 = s;
-    const double resid = nf_fma(-s, s, q);                 // exact: q - s*s
-    const double sl = (s > 0.0) ? nf_mul(resid, nf_mul(0.5, approx_rsqrt(q))) : 0.0;
+    const double resid = nf_fma(-s, s, q);                  // exact: q - s*s
+    const double sl = regular ? nf_mul(resid, hr) : 0.0;    // sqrt(q) = s + sl (+ O(2^-105))
     // q^1.5
     const double h1 = nf_mul(q, s);
-    double l1 = nf_fma(q, s, -h1);                         // exact low part of q*s
+    double l1 = nf_fma(q, s, -h1);                          // exact low part of q*s
     l1 = nf_fma(q, sl, l1);
     p15 = nf_add(h1, l1);
     // q^2.5
     const double qh = nf_mul(q, q);
-    const double ql = nf_fma(q, q, -qh);                   // exact low part of q*q
+    const double ql = nf_fma(q, q, -qh);                    // exact low part of q*q
     const double h2 = nf_mul(qh, s);
     double l2 = nf_fma(qh, s, -h2);
     l2 = nf_fma(qh, sl, l2);
     l2 = nf_fma(ql, s, l2);
     p25 = nf_add(h2, l2);
-    if (!(fabs(h1) < 1.0e300)) p15 = h1;                   // overflow / inf / nan: plain product
+    if (!(fabs(h1) < 1.0e300)) p15 = h1;                    // overflow / inf / nan: plain product
     if (!(fabs(h2) < 1.0e300)) p25 = h2;
+    const double r2 = nf_mul(r, r);
+    r05 = r;
+    r15 = nf_mul(r, r2);
+    r25 = nf_mul(r15, r2);
+}
+
+GFK_HD void strict_powers(double q, double& p05, double& p15, double& p25) {
+    double r05, r15, r25;
+    strict_powers_r(q, p05, p15, p25, r05, r15, r25);
 }
 
 // numpy's pairwise summation of the d products sx_k * sy_k (np.sum over the contiguous
@@ -145,6 +191,18 @@ GFK_HD double pairwise_dot(const AX& sx, const AY& sy, int d) {
     return nf_add(0.0, ret);
 }
 
+// From the four sums to the kernel value, numpy's order:
+//   s1 = sum (lambda r) r, s2 = sum (lambda^2 r) r, s3 = sum (lambda (sx - sy)) r, s4 = sum sx sy
+GFK_HD double strict_finish(double s1, double s2, double s3, double s4, const KParams& kp) {
+    const double qf = nf_add(kp.c, s1);
+    double p05, p15, p25, r05, r15, r25;
+    strict_powers_r(qf, p05, p15, p25, r05, r15, r25);
+    const double t1 = div_markstein(nf_mul(-3.0, s2), p25, r25);
+    const double t2 = div_markstein(nf_add(kp.trace, s3), p15, r15);
+    const double t3 = div_markstein(s4, p05, r05);
+    return nf_add(nf_add(t1, t2), t3);
+}
+
 // ---- strict pair kernel (float64) ------------------------------------------------------------
 // x, y, sx, sy: anything indexable by [k] (register arrays, strided shared-memory views).
 // Returns k(x, y) WITHOUT the gradient-free weight.
@@ -172,13 +230,22 @@ GFK_HD double pair_strict(const AX& x, const AY& y, const ASX& sx, const ASY& sy
     } else {
         s4 = pairwise_dot(sx, sy, d);
     }
-    const double qf = nf_add(kp.c, s1);
-    double p05, p15, p25;
-    strict_powers(qf, p05, p15, p25);
-    const double t1 = nf_div(nf_mul(-3.0, s2), p25);
-    const double t2 = nf_div(nf_add(kp.trace, s3), p15);
-    const double t3 = nf_div(s4, p05);
-    return nf_add(nf_add(t1, t2), t3);
+    return strict_finish(s1, s2, s3, s4, kp);
+}
+
+// From the dot products to the kernel value, FMA formulation:
+//   scalar: rr = <r, r>, su = <sx - sy, r>;  dense: rr = <L r, r>, uu = <L r, L r>, su = <sx - sy, L r>;  ss = <sx, sy>
+template <typename T, bool DENSE>
+GFK_HD T fast_finish(T rr, T uu, T su, T ss, const KParams& kp) {
+    const T lam = T(kp.lambda);
+    const T qf = DENSE ? (T(kp.c) + rr) : fma_t(lam, rr, T(kp.c));
+    const T n1 = DENSE ? (T(-3) * uu) : (T(-3) * T(kp.lambda_sq) * rr);
+    const T n2 = DENSE ? (T(kp.trace) + su) : fma_t(lam, su, T(kp.trace));
+    const T i1 = approx_rsqrt(qf);
+    const T i2 = i1 * i1;
+    const T i3 = i1 * i2;
+    const T i5 = i3 * i2;
+    return fma_t(n1, i5, fma_t(n2, i3, ss * i1));
 }
 
 // ---- fast pair kernel (float64 or float32) ------------------------------------------------------
@@ -206,15 +273,7 @@ GFK_HD T pair_fast(const AX& x, const AY& y, const ASX& sx, const ASY& sy, const
         }
         ss = fma_t(T(sx[k]), T(sy[k]), ss);
     }
-    const T lam = T(kp.lambda);
-    const T qf = DENSE ? (T(kp.c) + rr) : fma_t(lam, rr, T(kp.c));
-    const T n1 = DENSE ? (T(-3) * uu) : (T(-3) * T(kp.lambda_sq) * rr);
-    const T n2 = DENSE ? (T(kp.trace) + su) : fma_t(lam, su, T(kp.trace));
-    const T i1 = approx_rsqrt(qf);
-    const T i2 = i1 * i1;
-    const T i3 = i1 * i2;
-    const T i5 = i3 * i2;
-    return fma_t(n1, i5, fma_t(n2, i3, ss * i1));
+    return fast_finish<T, DENSE>(rr, uu, su, ss, kp);
 }
 
 // ---- (value, index) with numpy.argmin semantics ---------------------------------------------------

@@ -29,6 +29,10 @@ struct __align__(16) ThinWs {
     unsigned counter;        // last-block-done ticket / persistent-kernel barrier arrivals
     unsigned step;           // greedy step whose winner is in recv[]
     unsigned abort;          // persistent kernel: a barrier spin ran out (never expected)
+    unsigned pad_;
+    // persistent kernel, flag-in-data slots: every 8-byte word carries (tag << 32 | payload), so a reader
+    // that sees the expected tag in all three words has the whole record - no fences, no atomics
+    unsigned long long ll[2][kMaxBlocks / 2][4];
 };
 
 template <typename T>
@@ -319,6 +323,150 @@ __global__ void thin_step_tiled_kernel(ThinArgs<T> a) {
     grid_argmin_publish(bv, bi, a.ws, a.n_ranks);
 }
 
+// ---- one greedy step, runtime d, chunked: [256 rows] x [KC dims] slabs through shared memory ---------
+// Each row contributes KC consecutive values (one 128-byte line in float64) to a slab, so the global
+// loads are fully coalesced for any d; thread t owns row t of the tile and carries its running sums
+// across the slabs in registers, in numpy's order (sequential s1..s3, eight strided accumulators for s4
+// when d >= 8), so the strict mode stays bit-faithful for d <= 128.
+constexpr int kChunkK = 16;
+constexpr int kChunkLd = kChunkK + 1;
+
+template <typename T, bool STRICT, bool DENSE>
+__global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    const int d = a.kp.d;
+    T* ysh = reinterpret_cast<T*>(csm);
+    T* sysh = ysh + d;
+    T* ylsh = sysh + d;
+    T* xt = ylsh + d;
+    T* st = xt + kThreads * kChunkLd;
+    T* xlt = st + kThreads * kChunkLd;
+
+    const Cand win = pick_winner(a.ws, a.n_ranks);
+    const long long sel = (long long)win.i;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.idx_out[a.ws->step] = (uint32_t)sel;
+        a.ws->step += 1;
+    }
+    for (int k = threadIdx.x; k < d; k += kThreads) {
+        ysh[k] = __ldg(a.x + sel * d + k);
+        sysh[k] = __ldg(a.s + sel * d + k);
+        ylsh[k] = DENSE ? __ldg(a.xl + sel * d + k) : T(0);
+    }
+    T lwy = T(0), wy = T(0);
+    if (a.lw) {
+        lwy = __ldg(a.lw + sel);
+        if (!STRICT && a.w) wy = __ldg(a.w + sel);
+    }
+    double bv = __longlong_as_double(0x7ff0000000000000LL);
+    unsigned bi = 0xffffffffu;
+    const long long rows = a.row_end - a.row_begin;
+    const int d8 = d - (d % 8);                     // numpy's pairwise main region
+    for (long long base = (long long)blockIdx.x * kThreads; base < rows; base += (long long)gridDim.x * kThreads) {
+        const int tile_rows = (int)min((long long)kThreads, rows - base);
+        const bool active = (int)threadIdx.x < tile_rows;
+        const long long li = base + threadIdx.x;
+        // running sums of this thread's row
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;          // strict
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0;
+        T rr = T(0), uu = T(0), su = T(0), ss = T(0);             // fast
+        for (int k0 = 0; k0 < d; k0 += kChunkK) {
+            const int kc = min(kChunkK, d - k0);
+            __syncthreads();                                      // previous slab consumed; y row visible
+            for (int e = threadIdx.x; e < tile_rows * kChunkK; e += kThreads) {
+                const int r = e / kChunkK, k = e - r * kChunkK;
+                if (k < kc) {
+                    const long long g = (a.row_begin + base + r) * d + k0 + k;
+                    xt[r * kChunkLd + k] = __ldg(a.x + g);
+                    st[r * kChunkLd + k] = __ldg(a.s + g);
+                    if (DENSE) xlt[r * kChunkLd + k] = __ldg(a.xl + g);
+                }
+            }
+            __syncthreads();
+            if (active) {
+                const T* xr = xt + threadIdx.x * kChunkLd;
+                const T* sr = st + threadIdx.x * kChunkLd;
+                const T* xlr = xlt + threadIdx.x * kChunkLd;
+                if constexpr (STRICT) {
+                    for (int k = 0; k < kc; ++k) {
+                        const double r = nf_sub(xr[k], ysh[k0 + k]);
+                        const double pa = nf_mul(nf_mul(a.kp.lambda, r), r);
+                        const double pb = nf_mul(nf_mul(a.kp.lambda_sq, r), r);
+                        const double pc = nf_mul(nf_mul(a.kp.lambda, nf_sub(sr[k], sysh[k0 + k])), r);
+                        if (k0 + k == 0) { s1 = pa; s2 = pb; s3 = pc; }
+                        else { s1 = nf_add(s1, pa); s2 = nf_add(s2, pb); s3 = nf_add(s3, pc); }
+                    }
+                    if (d < 8) {
+                        for (int k = 0; k < kc; ++k) {
+                            const double p = nf_mul(sr[k], sysh[k0 + k]);
+                            s4 = (k0 + k == 0) ? p : nf_add(s4, p);
+                        }
+                    } else {
+                        // groups of 8 inside the main region [0, d8); the tail [d8, d) is added after the tree
+                        int k = 0;
+                        for (; k + 8 <= kc && k0 + k + 8 <= d8; k += 8) {
+                            const double p0 = nf_mul(sr[k + 0], sysh[k0 + k + 0]), p1 = nf_mul(sr[k + 1], sysh[k0 + k + 1]);
+                            const double p2 = nf_mul(sr[k + 2], sysh[k0 + k + 2]), p3 = nf_mul(sr[k + 3], sysh[k0 + k + 3]);
+                            const double p4 = nf_mul(sr[k + 4], sysh[k0 + k + 4]), p5 = nf_mul(sr[k + 5], sysh[k0 + k + 5]);
+                            const double p6 = nf_mul(sr[k + 6], sysh[k0 + k + 6]), p7 = nf_mul(sr[k + 7], sysh[k0 + k + 7]);
+                            if (k0 + k == 0) { r0 = p0; r1 = p1; r2 = p2; r3 = p3; r4 = p4; r5 = p5; r6 = p6; r7 = p7; }
+                            else {
+                                r0 = nf_add(r0, p0); r1 = nf_add(r1, p1); r2 = nf_add(r2, p2); r3 = nf_add(r3, p3);
+                                r4 = nf_add(r4, p4); r5 = nf_add(r5, p5); r6 = nf_add(r6, p6); r7 = nf_add(r7, p7);
+                            }
+                        }
+                        if (k0 + k >= d8 && k < kc) {
+                            if (k0 + k == d8)
+                                s4 = nf_add(nf_add(nf_add(r0, r1), nf_add(r2, r3)), nf_add(nf_add(r4, r5), nf_add(r6, r7)));
+                            for (; k < kc; ++k) s4 = nf_add(s4, nf_mul(sr[k], sysh[k0 + k]));
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (int k = 0; k < kc; ++k) {
+                        const T r = xr[k] - ysh[k0 + k];
+                        const T ds = sr[k] - sysh[k0 + k];
+                        if (DENSE) {
+                            const T u = xlr[k] - ylsh[k0 + k];
+                            rr = fma_t(u, r, rr);
+                            uu = fma_t(u, u, uu);
+                            su = fma_t(ds, u, su);
+                        } else {
+                            rr = fma_t(r, r, rr);
+                            su = fma_t(ds, r, su);
+                        }
+                        ss = fma_t(sr[k], sysh[k0 + k], ss);
+                    }
+                }
+            }
+        }
+        if (active) {
+            const long long i = a.row_begin + li;
+            double k;
+            if constexpr (STRICT) {
+                if (d >= 8) {
+                    if (d8 == d) s4 = nf_add(nf_add(nf_add(r0, r1), nf_add(r2, r3)), nf_add(nf_add(r4, r5), nf_add(r6, r7)));
+                    s4 = nf_add(0.0, s4);
+                }
+                k = strict_finish(s1, s2, s3, s4, a.kp);
+            } else {
+                k = (double)fast_finish<T, DENSE>(rr, uu, su, ss, a.kp);
+            }
+            double v;
+            const double av = a.A[li];
+            if constexpr (STRICT) {
+                if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, lwy, wy), k);
+                v = __dadd_rn(av, __dmul_rn(2.0, k));
+            } else {
+                v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, lwy, wy), k, av) : fma(2.0, k, av);
+            }
+            a.A[li] = v;
+            if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
+        }
+    }
+    grid_argmin_publish(bv, bi, a.ws, a.n_ranks);
+}
+
 // ---- all m greedy steps in ONE cooperative launch (single rank, small D) -------------------------------
 // One CTA per SM (or fewer for small shards).  Thread g of the grid owns rows g, g + T, g + 2T, ... for the
 // whole job (T = threads in the grid).  The running objective A and the log-weights of the owned rows live
@@ -335,7 +483,7 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
 }
 
 template <typename T, int D, bool STRICT, bool RESIDENT>
-__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt) {
+__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int ll_barrier) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double sv[32];
     __shared__ unsigned si[32];
@@ -394,8 +542,49 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
 
     for (int step = 0; step < m; ++step) {
         // ---- grid-wide argmin of the running objective ----------------------------------------------
-        Cand* partial = (step & 1) ? partial1 : partial0;
         block_argmin(bv, bi, sv, si);
+        if (ll_barrier) {
+            // flag-in-data exchange: 3 tagged 8-byte words per CTA, polled by warp 0 of every CTA
+            const unsigned long long tag = (unsigned long long)(unsigned)(step + 1) << 32;
+            unsigned long long (*slots_ll)[4] = ws->ll[step & 1];
+            if (tid == 0) {
+                const unsigned long long vb = (unsigned long long)__double_as_longlong(bv);
+                volatile unsigned long long* w = slots_ll[blockIdx.x];
+                w[0] = tag | (vb & 0xffffffffull);
+                w[1] = tag | (vb >> 32);
+                w[2] = tag | (unsigned long long)bi;
+            }
+            if (tid < 32) {
+                double wv = __longlong_as_double(0x7ff0000000000000LL);
+                unsigned wi = 0xffffffffu;
+                bool dead = false;
+                for (unsigned b = tid; b < gridDim.x && !dead; b += 32) {
+                    const volatile unsigned long long* w = slots_ll[b];
+                    unsigned long long w0, w1, w2;
+                    unsigned spins = 0;
+                    for (;;) {
+                        w0 = w[0]; w1 = w[1]; w2 = w[2];
+                        if ((w0 >> 32) == (tag >> 32) && (w1 >> 32) == (tag >> 32) && (w2 >> 32) == (tag >> 32)) break;
+                        if (++spins > kSpinLimit || ld_volatile_u32(&ws->abort)) { dead = true; break; }
+                    }
+                    const double pv = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+                    const unsigned pi = (unsigned)(w2 & 0xffffffffull);
+                    if (cand_better(pv, pi, wv, wi)) { wv = pv; wi = pi; }
+                }
+                if (__any_sync(0xffffffffu, dead)) { if (tid == 0) { abort_sh = 1; ws->abort = 1; } }
+                warp_argmin(wv, wi);
+                if (tid == 0) {
+                    win_sh = wi;
+                    if (blockIdx.x == 0) {
+                        a.idx_out[step] = wi;
+                        if (step == m - 1) { ws->send.v = wv; ws->send.i = wi; ws->recv[0] = ws->send; ws->step = (unsigned)m; }
+                    }
+                }
+            }
+            __syncthreads();
+            if (abort_sh) break;
+        } else {
+        Cand* partial = (step & 1) ? partial1 : partial0;
         if (tid == 0) {
             partial[blockIdx.x].v = bv;
             partial[blockIdx.x].i = bi;
@@ -428,6 +617,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
             }
         }
         __syncthreads();
+        }
         if (step == m - 1) break;
         const long long sel = (long long)win_sh;
 
@@ -496,6 +686,8 @@ __global__ void thin_reset_kernel(ThinWs* ws) {
         ws->step = 0;
         ws->abort = 0;
     }
+    unsigned long long* ll = &ws->ll[0][0][0];
+    for (int e = threadIdx.x; e < 2 * (kMaxBlocks / 2) * 4; e += blockDim.x) ll[e] = 0ull;
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -526,6 +718,10 @@ static int launch_step(const ThinArgs<T>& a, int d, cudaStream_t st, int grid_sm
         thin_step_small_kernel<T, 1, STRICT, 4><<<grid_small, kThreads, 0, st>>>(a);
     } else if (!dense && d == 3) {
         thin_step_small_kernel<T, 3, STRICT, 2><<<grid_small, kThreads, 0, st>>>(a);
+    } else if (tiled_threads == 0) {
+        const size_t smem = sizeof(T) * (size_t)(3 * d + (dense ? 3 : 2) * kThreads * kChunkLd);
+        if (dense) thin_step_chunked_kernel<T, STRICT, !STRICT><<<grid_tiled, kThreads, smem, st>>>(a);
+        else thin_step_chunked_kernel<T, STRICT, false><<<grid_tiled, kThreads, smem, st>>>(a);
     } else {
         thin_step_tiled_kernel<T, STRICT><<<grid_tiled, tiled_threads, tiled_smem, st>>>(a);
     }
@@ -558,8 +754,10 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
     if (env && env[0] == '0') use_resident = false;
     const size_t smem = use_resident ? resident : base;
     ThinArgs<T> args = a;
-    int m_arg = m, rpt_arg = rpt;
-    void* params[] = {&args, &m_arg, &rpt_arg};
+    int m_arg = m, rpt_arg = rpt, ll_arg = 1;
+    const char* benv = getenv("GFK_BARRIER");
+    if (benv && benv[0] == '0') ll_arg = 0;
+    void* params[] = {&args, &m_arg, &rpt_arg, &ll_arg};
     const void* fn = use_resident ? (const void*)thin_persistent_kernel<T, D, STRICT, true>
                                   : (const void*)thin_persistent_kernel<T, D, STRICT, false>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -571,7 +769,7 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
         cudaGetLastError();
         return 0;
     }
-    thin_reset_kernel<<<1, 32, 0, st>>>(a.ws);
+    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws);
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kPersistThreads), params, smem, st);
     if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
     count_launches(2);
@@ -615,7 +813,16 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     int tiled_threads = 0;
     size_t tiled_smem = 0;
     const bool uses_tiled = (a.xl != nullptr) || !(d >= 1 && d <= 4);
-    if (uses_tiled) {
+    // generic d: the chunked kernel, except strict d > 128 (numpy's recursive pairwise order needs the
+    // whole row at once) or y rows too long for its shared memory -> the row-tiled kernel
+    const size_t chunked_smem = sizeof(T) * (size_t)(3 * d + (a.xl ? 3 : 2) * kThreads * kChunkLd);
+    const bool use_chunked = uses_tiled && !(STRICT && d > 128) && chunked_smem <= 200 * 1024;
+    if (uses_tiled && use_chunked) {
+        if (a.xl) GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_kernel<T, STRICT, !STRICT>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunked_smem));
+        else GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_kernel<T, STRICT, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunked_smem));
+    } else if (uses_tiled) {
         int rc = tiled_config<T>(d, a.xl != nullptr, tiled_threads, tiled_smem);
         if (rc != GFK_OK) return rc;
         GFK_CUDA(cudaFuncSetAttribute(thin_step_tiled_kernel<T, STRICT>,
@@ -636,9 +843,11 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     }
     const int grid_init = grid_for(kThreads, 8);
     const int grid_small = grid_for(kThreads * 2, 4);
-    const int grid_tiled = uses_tiled ? grid_for(tiled_threads, tiled_smem > 50 * 1024 ? 2 : 4) : 1;
+    const int grid_tiled = !uses_tiled ? 1
+                           : use_chunked ? grid_for(kThreads, chunked_smem > 72 * 1024 ? 2 : 3)
+                                         : grid_for(tiled_threads, tiled_smem > 50 * 1024 ? 2 : 4);
 
-    thin_reset_kernel<<<1, 32, 0, st>>>(a.ws);
+    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws);
     thin_init_kernel<T, STRICT><<<grid_init, kThreads, 0, st>>>(a);
     GFK_CHECK_LAUNCH();
     for (int step = 1; step <= m; ++step) {

@@ -78,7 +78,7 @@ def test_reference_glue_fixtures(api, g45):
 
 
 # ---- seeded parity against the oracle -----------------------------------------------------------------
-@pytest.mark.parametrize('d', [1, 2, 3, 4, 5, 8, 10, 16, 33, 64])
+@pytest.mark.parametrize('d', [1, 2, 3, 4, 5, 7, 8, 9, 10, 12, 16, 20, 33, 64, 128, 130, 200])
 @pytest.mark.parametrize('pre', ['id', 'med'])
 def test_thin_indices_match_oracle(api, d, pre):
     rng = np.random.default_rng(1000 + d)

@@ -16,11 +16,16 @@ SO = os.path.join(HERE, 'host', 'libpair_check.so')
 P = ctypes.POINTER(ctypes.c_double)
 
 
-@pytest.fixture(scope='module')
-def hostlib():
-    if not os.path.exists(SO):
+SO_PERTURBED = os.path.join(HERE, 'host', 'libpair_check_perturbed.so')
+
+
+@pytest.fixture(scope='module', params=['exact-rsqrt', 'rsqrt-off-by-up-to-4ulp'])
+def hostlib(request):
+    """The second build perturbs the approximate reciprocal square root by -3..+4 ulp, as a device
+    approximation may be off: every result below must be unchanged (the corrections absorb it)."""
+    if not (os.path.exists(SO) and os.path.exists(SO_PERTURBED)):
         subprocess.run(['bash', os.path.join(HERE, 'host', 'build.sh')], check=True)
-    return ctypes.CDLL(SO)
+    return ctypes.CDLL(SO if request.param == 'exact-rsqrt' else SO_PERTURBED)
 
 
 def _p(a):
@@ -80,6 +85,24 @@ def test_strict_pair_is_numpy_order(hostlib, d, broadcast):
     fast = _call(hostlib.host_pair_fast, x, y, sx, sy, lam, lam2, tr)
     scale = np.abs(ref) + 1e-3 * np.max(np.abs(ref))
     assert np.max(np.abs(fast - ref) / scale) < 1e-11
+
+
+def test_markstein_division_is_ieee(hostlib):
+    # t3 = s4 / sqrt(qf) with random numerators: strict quotients must equal IEEE division
+    rng = np.random.default_rng(77)
+    n = 20000
+    x = rng.standard_normal((n, 1)) * np.exp(rng.normal(0, 2, (n, 1)))
+    y = np.zeros((1, 1))
+    sx = rng.standard_normal((n, 1)) * np.exp(rng.normal(0, 4, (n, 1)))
+    sy = np.ones((1, 1))
+    got = _call(hostlib.host_pair_strict, x, y, sx, sy, 1.0, 1.0, 0.0)
+    # direct: with trace = 0 the kernel is (-3 r^2 / q^2.5 + sx*r / q^1.5) + sx / q^0.5 in numpy's order
+    r = x[:, 0] - 0.0
+    q = 1.0 + (1.0 * r) * r
+    t1 = (-3.0 * ((1.0 * r) * r)) / _cr_pow(q, 2.5)
+    t2 = (0.0 + (1.0 * (sx[:, 0] - 1.0)) * r) / _cr_pow(q, 1.5)
+    t3 = (sx[:, 0] * 1.0) / np.sqrt(q)
+    assert np.array_equal(got, (t1 + t2) + t3)
 
 
 def test_pairwise_dot_is_numpy_pairwise(hostlib):
