@@ -373,13 +373,25 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
         for (int k0 = 0; k0 < d; k0 += kChunkK) {
             const int kc = min(kChunkK, d - k0);
             __syncthreads();                                      // previous slab consumed; y row visible
-            for (int e = threadIdx.x; e < tile_rows * kChunkK; e += kThreads) {
-                const int r = e / kChunkK, k = e - r * kChunkK;
-                if (k < kc) {
-                    const long long g = (a.row_begin + base + r) * d + k0 + k;
-                    xt[r * kChunkLd + k] = __ldg(a.x + g);
-                    st[r * kChunkLd + k] = __ldg(a.s + g);
-                    if (DENSE) xlt[r * kChunkLd + k] = __ldg(a.xl + g);
+            {
+                // thread t stages column (t % 16) of rows (t / 16) + 16 j: all 2 x 16 loads are independent
+                const int kk = threadIdx.x % kChunkK, r0 = threadIdx.x / kChunkK;
+                T xv[kChunkK], sv[kChunkK], lv[DENSE ? kChunkK : 1];
+                const long long g0 = (a.row_begin + base + r0) * d + k0 + kk;
+#pragma unroll
+                for (int j = 0; j < kChunkK; ++j) {
+                    const bool ok = (kk < kc) && (r0 + j * (kThreads / kChunkK) < tile_rows);
+                    const long long g = g0 + (long long)j * (kThreads / kChunkK) * d;
+                    xv[j] = ok ? __ldg(a.x + g) : T(0);
+                    sv[j] = ok ? __ldg(a.s + g) : T(0);
+                    if (DENSE) lv[j] = ok ? __ldg(a.xl + g) : T(0);
+                }
+#pragma unroll
+                for (int j = 0; j < kChunkK; ++j) {
+                    const int r = r0 + j * (kThreads / kChunkK);
+                    xt[r * kChunkLd + kk] = xv[j];
+                    st[r * kChunkLd + kk] = sv[j];
+                    if (DENSE) xlt[r * kChunkLd + kk] = lv[j];
                 }
             }
             __syncthreads();
@@ -475,15 +487,16 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
 // row - otherwise x / s are re-read each step through L2 (no HBM traffic once the 126 MB L2 holds them).
 // Per step: local update + argmin -> block argmin -> partial[parity][cta] -> grid barrier (arrival counter)
 // -> every CTA reduces the <= 148 partials itself (no second barrier) -> next selected row.
-constexpr int kPersistThreads = 512;
+constexpr int kPersistThreads = 512;      // default block size
+constexpr int kPersistMaxThreads = 768;   // launch bound (GFK_PTHREADS may raise the block size to this)
 constexpr unsigned kSpinLimit = 1u << 27;
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     return *reinterpret_cast<const volatile unsigned*>(p);
 }
 
-template <typename T, int D, bool STRICT, bool RESIDENT>
-__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int ll_barrier) {
+template <typename T, int D, bool STRICT, bool RESIDENT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int ll_barrier) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double sv[32];
     __shared__ unsigned si[32];
@@ -629,38 +642,51 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         if (a.lw) lwy = use_w ? __ldg(a.w + sel) : __ldg(a.lw + sel);
         bv = __longlong_as_double(0x7ff0000000000000LL);
         bi = 0xffffffffu;
-#pragma unroll 2
-        for (int j = 0; j < rpt; ++j) {
-            const long long li = (long long)j * TT + gt;
-            const int slot = j * nthr + tid;
-            if (li < rows) {
-                const long long i = a.row_begin + li;
-                T xr[D], sr[D];
-                if (RESIDENT) {
+        for (int j = 0; j < rpt; j += 2) {
+            // two owned rows in flight: loads first, then both kernels, then both stores
+            long long li[2];
+            int slot[2];
+            bool ok[2];
+            T xr[2][D], sr[2][D];
+            double av[2], wgt[2];
 #pragma unroll
-                    for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots + slot]; sr[k] = ss[k * slots + slot]; }
-                } else {
-                    load_row<D>(a.x, i, xr);
-                    load_row<D>(a.s, i, sr);
-                }
-                double k;
-                if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
-                else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
-                double v;
-                const double av = A_sh[slot];
-                if constexpr (STRICT) {
-                    if (a.lw) k = __dmul_rn(exp((double)lw_sh[slot] + (double)lwy), k);
-                    v = __dadd_rn(av, __dmul_rn(2.0, k));
-                } else {
-                    if (a.lw) {
-                        const double wgt = use_w ? (double)(lw_sh[slot] * lwy) : exp((double)lw_sh[slot] + (double)lwy);
-                        v = fma(2.0 * wgt, k, av);
+            for (int u = 0; u < 2; ++u) {
+                li[u] = (long long)(j + u) * TT + gt;
+                slot[u] = (j + u) * nthr + tid;
+                ok[u] = (j + u < rpt) && (li[u] < rows);
+                if (ok[u]) {
+                    if (RESIDENT) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) { xr[u][k] = xs[k * slots + slot[u]]; sr[u][k] = ss[k * slots + slot[u]]; }
                     } else {
-                        v = fma(2.0, k, av);
+                        load_row<D>(a.x, a.row_begin + li[u], xr[u]);
+                        load_row<D>(a.s, a.row_begin + li[u], sr[u]);
+                    }
+                    av[u] = A_sh[slot[u]];
+                    wgt[u] = 1.0;
+                    if (a.lw) {
+                        if constexpr (STRICT) wgt[u] = exp((double)lw_sh[slot[u]] + (double)lwy);
+                        else wgt[u] = use_w ? (double)(lw_sh[slot[u]] * lwy) : exp((double)lw_sh[slot[u]] + (double)lwy);
                     }
                 }
-                A_sh[slot] = v;
-                if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (ok[u]) {
+                    double k;
+                    if constexpr (STRICT) k = pair_strict<D>(xr[u], y, sr[u], sy, a.kp);
+                    else k = (double)pair_fast<T, D, false>(xr[u], y, sr[u], sy, xr[u], y, a.kp);
+                    double v;
+                    if constexpr (STRICT) {
+                        if (a.lw) k = __dmul_rn(wgt[u], k);
+                        v = __dadd_rn(av[u], __dmul_rn(2.0, k));
+                    } else {
+                        v = a.lw ? fma(2.0 * wgt[u], k, av[u]) : fma(2.0, k, av[u]);
+                    }
+                    A_sh[slot[u]] = v;
+                    const unsigned gi = (unsigned)(a.row_begin + li[u]);
+                    if (cand_better(v, gi, bv, bi)) { bv = v; bi = gi; }
+                }
             }
         }
     }
@@ -739,12 +765,17 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (!coop) return 0;
     const int sms = sm_count();
-    long long grid = (rows + kPersistThreads - 1) / kPersistThreads;
+    int threads = kPersistThreads;
+    if (const char* tenv = getenv("GFK_PTHREADS")) {
+        const int t = atoi(tenv);
+        if (t >= 64 && t <= kPersistMaxThreads && t % 32 == 0) threads = t;
+    }
+    long long grid = (rows + threads - 1) / threads;
     if (grid > sms) grid = sms;
     if (grid > kMaxBlocks / 2) grid = kMaxBlocks / 2;
-    const long long TT = grid * kPersistThreads;
+    const long long TT = grid * threads;
     const int rpt = (int)((rows + TT - 1) / TT);
-    const size_t slots = (size_t)rpt * kPersistThreads;
+    const size_t slots = (size_t)rpt * threads;
     const size_t base = slots * (sizeof(double) + (a.lw ? sizeof(T) : 0));
     const size_t resident = base + 2 * (size_t)D * slots * sizeof(T);
     const size_t budget = (size_t)smem_optin - 1024;   // static shared of the kernel
@@ -758,19 +789,24 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
     const char* benv = getenv("GFK_BARRIER");
     if (benv && benv[0] == '0') ll_arg = 0;
     void* params[] = {&args, &m_arg, &rpt_arg, &ll_arg};
-    const void* fn = use_resident ? (const void*)thin_persistent_kernel<T, D, STRICT, true>
-                                  : (const void*)thin_persistent_kernel<T, D, STRICT, false>;
+    const void* fn;
+    if (threads > kPersistThreads)
+        fn = use_resident ? (const void*)thin_persistent_kernel<T, D, STRICT, true, kPersistMaxThreads>
+                          : (const void*)thin_persistent_kernel<T, D, STRICT, false, kPersistMaxThreads>;
+    else
+        fn = use_resident ? (const void*)thin_persistent_kernel<T, D, STRICT, true, kPersistThreads>
+                          : (const void*)thin_persistent_kernel<T, D, STRICT, false, kPersistThreads>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kPersistThreads, smem) != cudaSuccess || occ < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem) != cudaSuccess || occ < 1) {
         cudaGetLastError();
         return 0;
     }
     thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws);
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kPersistThreads), params, smem, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(threads), params, smem, st);
     if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
     count_launches(2);
     return 1;
