@@ -63,6 +63,27 @@ static int nccl_fail(int rc, const char* what) {
     return GFK_ENCCL;
 }
 
+// ---- peer mailboxes ---------------------------------------------------------------------------------
+static unsigned long long* g_mail_local = nullptr;
+static unsigned long long* g_mail_peer[kMailRanks] = {nullptr};
+static bool g_mail_open = false;
+static unsigned g_tag_epoch = 1;
+static unsigned g_job_count = 0;
+
+void p2p_next_job(MailArgs* out, int steps) {
+    memset(out, 0, sizeof(*out));
+    if (!g_mail_open) return;
+    out->enabled = 1;
+    out->local = g_mail_local;
+    for (int r = 0; r < kMailRanks; ++r) out->peer[r] = g_mail_peer[r];
+    // every rank makes the same sequence of jobs, so the epochs agree without communication
+    if (g_tag_epoch > 0xf0000000u - (unsigned)steps - 2u) g_tag_epoch = 1;   // wrap long before 2^32
+    out->tag_base = g_tag_epoch;
+    g_tag_epoch += (unsigned)steps + 2u;
+    out->job_parity = (int)(g_job_count++ & 1u);
+    out->rank = g_rank;
+}
+
 int comm_size() { return g_size; }
 int comm_rank() { return g_rank; }
 
@@ -116,7 +137,54 @@ extern "C" int gfk_allreduce_sum(double* buf, int64_t count, void* stream) {
     return rc == ncclSuccess ? GFK_OK : nccl_fail(rc, "ncclAllReduce");
 }
 
+extern "C" int gfk_p2p_local_handle(void* handle64_host) {
+    GFK_REQUIRE(handle64_host, "gfk_p2p_local_handle: NULL output");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!g_mail_local) {
+        GFK_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_mail_local), sizeof(unsigned long long) * kMailWords));
+        GFK_CUDA(cudaMemset(g_mail_local, 0, sizeof(unsigned long long) * kMailWords));
+        GFK_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    GFK_CUDA(cudaIpcGetMemHandle(&h, g_mail_local));
+    memcpy(handle64_host, &h, sizeof(h));
+    return GFK_OK;
+}
+
+extern "C" int gfk_p2p_open(const void* handles_host, int n_ranks, int rank) {
+    GFK_REQUIRE(handles_host && n_ranks >= 2 && n_ranks <= kMailRanks && rank >= 0 && rank < n_ranks,
+                "gfk_p2p_open: bad arguments");
+    GFK_REQUIRE(g_mail_local, "gfk_p2p_open: call gfk_p2p_local_handle first");
+    GFK_REQUIRE(n_ranks == g_size && rank == g_rank, "gfk_p2p_open: communicator mismatch (call gfk_comm_init first)");
+    const char* base = static_cast<const char*>(handles_host);
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == rank) { g_mail_peer[r] = g_mail_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, base + 64 * r, sizeof(h));
+        void* ptr = nullptr;
+        GFK_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        g_mail_peer[r] = static_cast<unsigned long long*>(ptr);
+    }
+    g_mail_open = true;
+    g_tag_epoch = 1;
+    g_job_count = 0;
+    return GFK_OK;
+}
+
+extern "C" int gfk_p2p_enabled(void) { return g_mail_open ? 1 : 0; }
+
 extern "C" int gfk_comm_finalize(void) {
+    if (g_mail_open) {
+        for (int r = 0; r < kMailRanks; ++r) {
+            if (g_mail_peer[r] && g_mail_peer[r] != g_mail_local) cudaIpcCloseMemHandle(g_mail_peer[r]);
+            g_mail_peer[r] = nullptr;
+        }
+        g_mail_open = false;
+    }
+    if (g_mail_local) {
+        cudaFree(g_mail_local);
+        g_mail_local = nullptr;
+    }
     if (g_comm) {
         g_api.CommDestroy(g_comm);
         g_comm = nullptr;

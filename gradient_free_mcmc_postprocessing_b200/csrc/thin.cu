@@ -48,6 +48,8 @@ struct ThinArgs {
     ThinWs* ws;
     uint32_t* idx_out;
     int n_ranks;
+    int step;        // multi-launch kernels: index of the exchange this launch produces (consumes step - 1)
+    MailArgs mail;   // peer mailboxes (enabled: exchange through them instead of NCCL)
 };
 
 // ---- row access -------------------------------------------------------------------------------
@@ -101,10 +103,74 @@ struct View {
     __device__ __forceinline__ T operator[](int k) const { return p[k]; }
 };
 
-__device__ __forceinline__ Cand pick_winner(const ThinWs* ws, int n_ranks) {
-    Cand best = ws->recv[0];
-    for (int r = 1; r < n_ranks; ++r) {
-        const Cand c = ws->recv[r];
+constexpr unsigned kSpinLimit = 1u << 27;
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+    return *reinterpret_cast<const volatile unsigned*>(p);
+}
+
+__device__ __forceinline__ int mail_offset(const MailArgs& m, int exchange, int rank) {
+    return (((m.job_parity * 2 + (exchange & 1)) * kMailRanks) + rank) * 4;
+}
+
+// lanes 0 .. n_ranks-1 of ONE warp: lane r stores this rank's candidate into rank r's mailbox (NVLink store
+// for r != rank).  Three tagged 8-byte words; no fence is needed because every word validates itself.
+__device__ __forceinline__ void mail_post(const MailArgs& m, int n_ranks, int exchange, double v, unsigned i,
+                                          int lane) {
+    if (lane < n_ranks) {
+        const unsigned long long tag = (unsigned long long)(m.tag_base + (unsigned)exchange + 1u) << 32;
+        const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+        volatile unsigned long long* w = m.peer[lane] + mail_offset(m, exchange, m.rank);
+        w[0] = tag | (vb & 0xffffffffull);
+        w[1] = tag | (vb >> 32);
+        w[2] = tag | (unsigned long long)i;
+    }
+}
+
+// a full warp: lane r polls slot r of the local mailbox until its three tags match, then the warp reduces
+// the candidates with numpy.argmin semantics.  Every lane returns the winner.  dead: a spin ran out.
+__device__ __forceinline__ Cand mail_wait(const MailArgs& m, int n_ranks, int exchange, int lane, bool& dead,
+                                          const unsigned* abort_flag) {
+    double v = __longlong_as_double(0x7ff0000000000000LL);
+    unsigned i = 0xffffffffu;
+    bool bad = false;
+    if (lane < n_ranks) {
+        const unsigned tag = m.tag_base + (unsigned)exchange + 1u;
+        const volatile unsigned long long* w = m.local + mail_offset(m, exchange, lane);
+        unsigned long long w0, w1, w2;
+        unsigned spins = 0;
+        for (;;) {
+            w0 = w[0]; w1 = w[1]; w2 = w[2];
+            if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && (unsigned)(w2 >> 32) == tag) break;
+            if (++spins > kSpinLimit || (abort_flag && ld_volatile_u32(abort_flag))) { bad = true; break; }
+        }
+        v = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+        i = (unsigned)(w2 & 0xffffffffull);
+    }
+    dead = __any_sync(0xffffffffu, bad);
+    warp_argmin(v, i);
+    Cand c;
+    c.v = v;
+    c.i = i;
+    return c;
+}
+
+// winner of exchange (a.step - 1): from the peer mailboxes (warp 0 polls, block broadcast) or from recv[]
+template <typename T>
+__device__ __forceinline__ Cand pick_winner(const ThinArgs<T>& a) {
+    if (a.mail.enabled && a.n_ranks > 1) {
+        __shared__ Cand win_bc;
+        if (threadIdx.x < 32) {
+            bool dead;
+            const Cand c = mail_wait(a.mail, a.n_ranks, a.step - 1, threadIdx.x, dead, nullptr);
+            if (threadIdx.x == 0) win_bc = c;
+        }
+        __syncthreads();
+        return win_bc;
+    }
+    Cand best = a.ws->recv[0];
+    for (int r = 1; r < a.n_ranks; ++r) {
+        const Cand c = a.ws->recv[r];
         if (cand_better(c.v, c.i, best.v, best.i)) best = c;
     }
     return best;
@@ -112,7 +178,10 @@ __device__ __forceinline__ Cand pick_winner(const ThinWs* ws, int n_ranks) {
 
 // grid-level argmin: block result -> partial[], last block reduces partial[] -> ws->send
 // (single rank: the exchange is the identity, so the result goes straight into recv[0])
-__device__ __forceinline__ void grid_argmin_publish(double v, unsigned i, ThinWs* ws, int n_ranks) {
+template <typename T>
+__device__ __forceinline__ void grid_argmin_publish(double v, unsigned i, const ThinArgs<T>& a) {
+    ThinWs* ws = a.ws;
+    const int n_ranks = a.n_ranks;
     __shared__ double sv[32];
     __shared__ unsigned si[32];
     __shared__ bool is_last;
@@ -135,7 +204,8 @@ __device__ __forceinline__ void grid_argmin_publish(double v, unsigned i, ThinWs
         if (cand_better(pv, pi, bv, bi)) { bv = pv; bi = pi; }
     }
     __syncthreads();
-    block_argmin(bv, bi, sv, si);
+    block_argmin(bv, bi, sv, si);      // every lane of warp 0 holds the result
+    if (a.mail.enabled && n_ranks > 1 && threadIdx.x < 32) mail_post(a.mail, n_ranks, a.step, bv, bi, threadIdx.x);
     if (threadIdx.x == 0) {
         ws->send.v = bv;
         ws->send.i = bi;
@@ -184,18 +254,15 @@ __global__ void __launch_bounds__(kThreads) thin_init_kernel(ThinArgs<T> a) {
         a.A[li] = k;
         if (cand_better(k, (unsigned)i, bv, bi)) { bv = k; bi = (unsigned)i; }
     }
-    grid_argmin_publish(bv, bi, a.ws, a.n_ranks);
+    grid_argmin_publish(bv, bi, a);
 }
 
 // ---- one greedy step, compile-time small D: rows live in registers ----------------------------------
 template <typename T, int D, bool STRICT, int ITEMS>
 __global__ void __launch_bounds__(kThreads) thin_step_small_kernel(ThinArgs<T> a) {
-    const Cand win = pick_winner(a.ws, a.n_ranks);
+    const Cand win = pick_winner(a);
     const long long sel = (long long)win.i;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        a.idx_out[a.ws->step] = (uint32_t)sel;
-        a.ws->step += 1;
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
     T y[D], sy[D];
     load_row<D>(a.x, sel, y);
     load_row<D>(a.s, sel, sy);
@@ -243,7 +310,7 @@ __global__ void __launch_bounds__(kThreads) thin_step_small_kernel(ThinArgs<T> a
             }
         }
     }
-    grid_argmin_publish(bv, bi, a.ws, a.n_ranks);
+    grid_argmin_publish(bv, bi, a);
 }
 
 // ---- one greedy step, runtime d: coalesced tile -> padded shared memory -> thread per row -----------
@@ -262,12 +329,9 @@ __global__ void thin_step_tiled_kernel(ThinArgs<T> a) {
     T* st = xt + (size_t)TR * ld;
     T* xlt = st + (size_t)TR * ld;
 
-    const Cand win = pick_winner(a.ws, a.n_ranks);
+    const Cand win = pick_winner(a);
     const long long sel = (long long)win.i;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        a.idx_out[a.ws->step] = (uint32_t)sel;
-        a.ws->step += 1;
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
     for (int k = threadIdx.x; k < d; k += TR) {
         ysh[k] = __ldg(a.x + sel * d + k);
         sysh[k] = __ldg(a.s + sel * d + k);
@@ -320,7 +384,7 @@ __global__ void thin_step_tiled_kernel(ThinArgs<T> a) {
             if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
         }
     }
-    grid_argmin_publish(bv, bi, a.ws, a.n_ranks);
+    grid_argmin_publish(bv, bi, a);
 }
 
 // ---- one greedy step, runtime d, chunked: [256 rows] x [KC dims] slabs through shared memory ---------
@@ -342,12 +406,9 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
     T* st = xt + kThreads * kChunkLd;
     T* xlt = st + kThreads * kChunkLd;
 
-    const Cand win = pick_winner(a.ws, a.n_ranks);
+    const Cand win = pick_winner(a);
     const long long sel = (long long)win.i;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        a.idx_out[a.ws->step] = (uint32_t)sel;
-        a.ws->step += 1;
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
     for (int k = threadIdx.x; k < d; k += kThreads) {
         ysh[k] = __ldg(a.x + sel * d + k);
         sysh[k] = __ldg(a.s + sel * d + k);
@@ -476,7 +537,7 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
             if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
         }
     }
-    grid_argmin_publish(bv, bi, a.ws, a.n_ranks);
+    grid_argmin_publish(bv, bi, a);
 }
 
 // ---- all m greedy steps in ONE cooperative launch (single rank, small D) -------------------------------
@@ -487,16 +548,10 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
 // row - otherwise x / s are re-read each step through L2 (no HBM traffic once the 126 MB L2 holds them).
 // Per step: local update + argmin -> block argmin -> partial[parity][cta] -> grid barrier (arrival counter)
 // -> every CTA reduces the <= 148 partials itself (no second barrier) -> next selected row.
-constexpr int kPersistThreads = 512;      // default block size
-constexpr int kPersistMaxThreads = 768;   // launch bound (GFK_PTHREADS may raise the block size to this)
-constexpr unsigned kSpinLimit = 1u << 27;
+constexpr int kPersistThreads = 512;
 
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
-    return *reinterpret_cast<const volatile unsigned*>(p);
-}
-
-template <typename T, int D, bool STRICT, bool RESIDENT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int ll_barrier) {
+template <typename T, int D, bool STRICT>
+__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double sv[32];
     __shared__ unsigned si[32];
@@ -510,12 +565,11 @@ __global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a
     const int slots = rpt * nthr;
     double* A_sh = reinterpret_cast<double*>(psm);
     T* lw_sh = reinterpret_cast<T*>(A_sh + slots);              // lw (strict / no w) or w (fast)
-    T* xs = lw_sh + (a.lw ? slots : 0);                          // RESIDENT: x as [D][slots], then s
-    T* ss = xs + (RESIDENT ? (size_t)D * slots : 0);
+    const int slots_res = rpt_res * nthr;                        // the first rpt_res rows of every thread
+    T* xs = lw_sh + (a.lw ? slots : 0);                          // resident x as [D][slots_res], then s
+    T* ss = xs + (size_t)D * slots_res;
     const bool use_w = (!STRICT && a.w != nullptr);
     ThinWs* ws = a.ws;
-    Cand* partial0 = ws->partial;
-    Cand* partial1 = ws->partial + kMaxBlocks / 2;
     if (tid == 0) abort_sh = 0;
 
     // ---- step 0: diagonal, and stage the owned rows ----------------------------------------------------
@@ -529,9 +583,9 @@ __global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a
             T xr[D], sr[D];
             load_row<D>(a.x, i, xr);
             load_row<D>(a.s, i, sr);
-            if (RESIDENT) {
+            if (j < rpt_res) {
 #pragma unroll
-                for (int k = 0; k < D; ++k) { xs[k * slots + slot] = xr[k]; ss[k * slots + slot] = sr[k]; }
+                for (int k = 0; k < D; ++k) { xs[k * slots_res + slot] = xr[k]; ss[k * slots_res + slot] = sr[k]; }
             }
             double k0;
             if constexpr (STRICT) k0 = pair_strict<D>(xr, xr, sr, sr, a.kp);
@@ -555,9 +609,11 @@ __global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a
 
     for (int step = 0; step < m; ++step) {
         // ---- grid-wide argmin of the running objective ----------------------------------------------
+        // flag-in-data exchange: each CTA publishes its block minimum as 3 tagged 8-byte words; warp 0 of
+        // every CTA polls all slots and reduces them itself, so there is no separate barrier, no atomic and
+        // no fence on the critical path.  Slots alternate by step parity (a CTA can be at most one step ahead).
         block_argmin(bv, bi, sv, si);
-        if (ll_barrier) {
-            // flag-in-data exchange: 3 tagged 8-byte words per CTA, polled by warp 0 of every CTA
+        {
             const unsigned long long tag = (unsigned long long)(unsigned)(step + 1) << 32;
             unsigned long long (*slots_ll)[4] = ws->ll[step & 1];
             if (tid == 0) {
@@ -584,9 +640,18 @@ __global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a
                     const unsigned pi = (unsigned)(w2 & 0xffffffffull);
                     if (cand_better(pv, pi, wv, wi)) { wv = pv; wi = pi; }
                 }
-                if (__any_sync(0xffffffffu, dead)) { if (tid == 0) { abort_sh = 1; ws->abort = 1; } }
+                dead = __any_sync(0xffffffffu, dead);
                 warp_argmin(wv, wi);
+                if (a.n_ranks > 1 && !dead) {
+                    // cross-GPU stage: CTA 0 stores this rank's winner into every peer's mailbox over NVLink;
+                    // every CTA polls the local mailbox for all ranks' winners and reduces them
+                    if (blockIdx.x == 0) mail_post(a.mail, a.n_ranks, step, wv, wi, tid);
+                    const Cand g = mail_wait(a.mail, a.n_ranks, step, tid, dead, &ws->abort);
+                    wv = g.v;
+                    wi = g.i;
+                }
                 if (tid == 0) {
+                    if (dead) { abort_sh = 1; ws->abort = 1; }
                     win_sh = wi;
                     if (blockIdx.x == 0) {
                         a.idx_out[step] = wi;
@@ -596,40 +661,6 @@ __global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a
             }
             __syncthreads();
             if (abort_sh) break;
-        } else {
-        Cand* partial = (step & 1) ? partial1 : partial0;
-        if (tid == 0) {
-            partial[blockIdx.x].v = bv;
-            partial[blockIdx.x].i = bi;
-            __threadfence();
-            atomicAdd(&ws->counter, 1u);
-            const unsigned target = (unsigned)(step + 1) * gridDim.x;
-            unsigned spins = 0;
-            while (ld_volatile_u32(&ws->counter) < target) {
-                if (++spins > kSpinLimit || ld_volatile_u32(&ws->abort)) { abort_sh = 1; ws->abort = 1; break; }
-            }
-            __threadfence();
-        }
-        __syncthreads();
-        if (abort_sh) break;
-        if (tid < 32) {
-            double wv = __longlong_as_double(0x7ff0000000000000LL);
-            unsigned wi = 0xffffffffu;
-            for (unsigned b = tid; b < gridDim.x; b += 32) {
-                const double pv = __ldcg(&partial[b].v);
-                const unsigned pi = (unsigned)__ldcg(&partial[b].i);
-                if (cand_better(pv, pi, wv, wi)) { wv = pv; wi = pi; }
-            }
-            warp_argmin(wv, wi);
-            if (tid == 0) {
-                win_sh = wi;
-                if (blockIdx.x == 0) {
-                    a.idx_out[step] = wi;
-                    if (step == m - 1) { ws->send.v = wv; ws->send.i = wi; ws->recv[0] = ws->send; ws->step = (unsigned)m; }
-                }
-            }
-        }
-        __syncthreads();
         }
         if (step == m - 1) break;
         const long long sel = (long long)win_sh;
@@ -642,51 +673,38 @@ __global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a
         if (a.lw) lwy = use_w ? __ldg(a.w + sel) : __ldg(a.lw + sel);
         bv = __longlong_as_double(0x7ff0000000000000LL);
         bi = 0xffffffffu;
-        for (int j = 0; j < rpt; j += 2) {
-            // two owned rows in flight: loads first, then both kernels, then both stores
-            long long li[2];
-            int slot[2];
-            bool ok[2];
-            T xr[2][D], sr[2][D];
-            double av[2], wgt[2];
+#pragma unroll 2
+        for (int j = 0; j < rpt; ++j) {
+            const long long li = (long long)j * TT + gt;
+            const int slot = j * nthr + tid;
+            if (li < rows) {
+                const long long i = a.row_begin + li;
+                T xr[D], sr[D];
+                if (j < rpt_res) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                li[u] = (long long)(j + u) * TT + gt;
-                slot[u] = (j + u) * nthr + tid;
-                ok[u] = (j + u < rpt) && (li[u] < rows);
-                if (ok[u]) {
-                    if (RESIDENT) {
-#pragma unroll
-                        for (int k = 0; k < D; ++k) { xr[u][k] = xs[k * slots + slot[u]]; sr[u][k] = ss[k * slots + slot[u]]; }
-                    } else {
-                        load_row<D>(a.x, a.row_begin + li[u], xr[u]);
-                        load_row<D>(a.s, a.row_begin + li[u], sr[u]);
-                    }
-                    av[u] = A_sh[slot[u]];
-                    wgt[u] = 1.0;
+                    for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots_res + slot]; sr[k] = ss[k * slots_res + slot]; }
+                } else {
+                    load_row<D>(a.x, i, xr);
+                    load_row<D>(a.s, i, sr);
+                }
+                double k;
+                if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
+                else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
+                double v;
+                const double av = A_sh[slot];
+                if constexpr (STRICT) {
+                    if (a.lw) k = __dmul_rn(exp((double)lw_sh[slot] + (double)lwy), k);
+                    v = __dadd_rn(av, __dmul_rn(2.0, k));
+                } else {
                     if (a.lw) {
-                        if constexpr (STRICT) wgt[u] = exp((double)lw_sh[slot[u]] + (double)lwy);
-                        else wgt[u] = use_w ? (double)(lw_sh[slot[u]] * lwy) : exp((double)lw_sh[slot[u]] + (double)lwy);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (ok[u]) {
-                    double k;
-                    if constexpr (STRICT) k = pair_strict<D>(xr[u], y, sr[u], sy, a.kp);
-                    else k = (double)pair_fast<T, D, false>(xr[u], y, sr[u], sy, xr[u], y, a.kp);
-                    double v;
-                    if constexpr (STRICT) {
-                        if (a.lw) k = __dmul_rn(wgt[u], k);
-                        v = __dadd_rn(av[u], __dmul_rn(2.0, k));
+                        const double wgt = use_w ? (double)(lw_sh[slot] * lwy) : exp((double)lw_sh[slot] + (double)lwy);
+                        v = fma(2.0 * wgt, k, av);
                     } else {
-                        v = a.lw ? fma(2.0 * wgt[u], k, av[u]) : fma(2.0, k, av[u]);
+                        v = fma(2.0, k, av);
                     }
-                    A_sh[slot[u]] = v;
-                    const unsigned gi = (unsigned)(a.row_begin + li[u]);
-                    if (cand_better(v, gi, bv, bi)) { bv = v; bi = gi; }
                 }
+                A_sh[slot] = v;
+                if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
             }
         }
     }
@@ -698,11 +716,12 @@ __global__ void __launch_bounds__(BLOCK, 1) thin_persistent_kernel(ThinArgs<T> a
 }
 
 // winner of the last exchange -> idx_out[m - 1]
-__global__ void thin_finish_kernel(ThinWs* ws, uint32_t* idx_out, int n_ranks) {
+template <typename T>
+__global__ void thin_finish_kernel(ThinArgs<T> a) {
+    const Cand win = pick_winner(a);
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const Cand win = pick_winner(ws, n_ranks);
-        idx_out[ws->step] = (uint32_t)win.i;
-        ws->step += 1;
+        a.idx_out[a.step - 1] = (uint32_t)win.i;
+        a.ws->step = (unsigned)a.step;
     }
 }
 
@@ -765,11 +784,7 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (!coop) return 0;
     const int sms = sm_count();
-    int threads = kPersistThreads;
-    if (const char* tenv = getenv("GFK_PTHREADS")) {
-        const int t = atoi(tenv);
-        if (t >= 64 && t <= kPersistMaxThreads && t % 32 == 0) threads = t;
-    }
+    const int threads = kPersistThreads;
     long long grid = (rows + threads - 1) / threads;
     if (grid > sms) grid = sms;
     if (grid > kMaxBlocks / 2) grid = kMaxBlocks / 2;
@@ -777,25 +792,19 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
     const int rpt = (int)((rows + TT - 1) / TT);
     const size_t slots = (size_t)rpt * threads;
     const size_t base = slots * (sizeof(double) + (a.lw ? sizeof(T) : 0));
-    const size_t resident = base + 2 * (size_t)D * slots * sizeof(T);
-    const size_t budget = (size_t)smem_optin - 1024;   // static shared of the kernel
-    bool use_resident = resident <= budget;
+    const size_t budget = (size_t)smem_optin - 1024;   // minus the kernel's static shared memory
     if (base > budget) return 0;
+    // as many of each thread's rows as fit stay in shared memory for the whole job; the rest stream via L2
+    const size_t per_row_slot = 2 * (size_t)D * threads * sizeof(T);
+    int rpt_res = (int)((budget - base) / per_row_slot);
+    if (rpt_res > rpt) rpt_res = rpt;
     const char* env = getenv("GFK_RESIDENT");
-    if (env && env[0] == '0') use_resident = false;
-    const size_t smem = use_resident ? resident : base;
+    if (env && env[0] == '0') rpt_res = 0;
+    const size_t smem = base + (size_t)rpt_res * per_row_slot;
     ThinArgs<T> args = a;
-    int m_arg = m, rpt_arg = rpt, ll_arg = 1;
-    const char* benv = getenv("GFK_BARRIER");
-    if (benv && benv[0] == '0') ll_arg = 0;
-    void* params[] = {&args, &m_arg, &rpt_arg, &ll_arg};
-    const void* fn;
-    if (threads > kPersistThreads)
-        fn = use_resident ? (const void*)thin_persistent_kernel<T, D, STRICT, true, kPersistMaxThreads>
-                          : (const void*)thin_persistent_kernel<T, D, STRICT, false, kPersistMaxThreads>;
-    else
-        fn = use_resident ? (const void*)thin_persistent_kernel<T, D, STRICT, true, kPersistThreads>
-                          : (const void*)thin_persistent_kernel<T, D, STRICT, false, kPersistThreads>;
+    int m_arg = m, rpt_arg = rpt, res_arg = rpt_res;
+    void* params[] = {&args, &m_arg, &rpt_arg, &res_arg};
+    const void* fn = (const void*)thin_persistent_kernel<T, D, STRICT>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -816,7 +825,7 @@ template <typename T, bool STRICT>
 static int try_persistent(const ThinArgs<T>& a, int d, int m, cudaStream_t st) {
     const char* env = getenv("GFK_PERSISTENT");
     if (env && env[0] == '0') return 0;
-    if (a.n_ranks != 1 || a.xl != nullptr) return 0;
+    if ((a.n_ranks != 1 && !a.mail.enabled) || a.xl != nullptr) return 0;
     switch (d) {
         case 1: return try_persistent_d<T, 1, STRICT>(a, m, st);
         case 2: return try_persistent_d<T, 2, STRICT>(a, m, st);
@@ -842,6 +851,12 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     a.ws = static_cast<ThinWs*>(ws_raw);
     a.idx_out = idx_out;
     a.n_ranks = comm_size();
+    a.step = 0;
+    p2p_next_job(&a.mail, m);
+    if (a.n_ranks == 1) a.mail.enabled = 0;
+    if (const char* penv = getenv("GFK_P2P")) {
+        if (penv[0] == '0') a.mail.enabled = 0;      // force the NCCL exchange (A/B measurements)
+    }
     const int d = p->d;
     const long long rows = row_end - row_begin;
     const int sms = sm_count();
@@ -884,18 +899,21 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
                                          : grid_for(tiled_threads, tiled_smem > 50 * 1024 ? 2 : 4);
 
     thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws);
+    a.step = 0;                                  // produces exchange 0
     thin_init_kernel<T, STRICT><<<grid_init, kThreads, 0, st>>>(a);
     GFK_CHECK_LAUNCH();
+    const bool nccl_exchange = a.n_ranks > 1 && !a.mail.enabled;
     for (int step = 1; step <= m; ++step) {
-        // exchange the candidates of step-1, then either continue or finish
-        if (a.n_ranks > 1) {
+        // exchange the candidates of step-1 (peer mailboxes: inside the kernels), then continue or finish
+        if (nccl_exchange) {
             int rc = comm_allgather16(&a.ws->send, a.ws->recv, st);
             if (rc != GFK_OK) return rc;
         }
+        a.step = step;                           // consumes exchange step-1, produces exchange step
         if (step == m) break;
         launch_step<T, STRICT>(a, d, st, grid_small, grid_tiled, tiled_threads, tiled_smem);
     }
-    thin_finish_kernel<<<1, 32, 0, st>>>(a.ws, idx_out, a.n_ranks);
+    thin_finish_kernel<T><<<1, 32, 0, st>>>(a);
     count_launches(2 + (long long)m);   // reset + init + (m - 1) steps + finish
     GFK_CHECK_LAUNCH();
     return GFK_OK;

@@ -48,7 +48,7 @@ def nccl_library_path():
     return None
 
 
-def init(group=None):
+def init(group=None, p2p=True):
     """Collective.  Creates the libgfk communicator mirroring the torch.distributed group."""
     import torch.distributed as dist
     lib = _lib.load()
@@ -72,7 +72,39 @@ def init(group=None):
             dist.broadcast(uid, src=0, group=group)
     raw = uid.numpy().tobytes()
     _lib.check(lib.gfk_comm_init(world, rank, raw, path_b))
+    if world > 1 and p2p and os.environ.get('GFK_P2P', '1') != '0':
+        _open_mailboxes(group, world, rank)
     return world, rank
+
+
+def _open_mailboxes(group, world, rank):
+    """Exchange CUDA IPC handles of the per-rank mailboxes so the thinning kernels can store their
+    per-step (value, index) candidates straight into peer memory over NVLink.  Collective."""
+    import warnings
+    import torch.distributed as dist
+    lib = _lib.load()
+    buf = (ctypes.c_char * 64)()
+    rc = lib.gfk_p2p_local_handle(buf)
+    mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32)
+    nccl = dist.get_backend(group) == 'nccl'
+    if nccl:
+        mine, ok = mine.cuda(), ok.cuda()
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 1:
+        handles = b''.join(g.cpu().numpy().tobytes() for g in gathered)
+        rc = lib.gfk_p2p_open(handles, world, rank)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32)
+        if nccl:
+            ok = ok.cuda()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) != 1:
+        # every rank must agree, otherwise some would wait on mailboxes nobody writes
+        os.environ['GFK_P2P'] = '0'
+        warnings.warn('CUDA IPC mailboxes unavailable (%s); using the NCCL all-gather exchange'
+                      % lib.gfk_last_error().decode('utf-8', 'replace'))
 
 
 def finalize():

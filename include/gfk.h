@@ -146,6 +146,14 @@ int gfk_pairs(const gfk_problem* p, const int64_t* ia, const int64_t* ib, int64_
  * nccl_path: path of libnccl.so.2 to dlopen, or NULL to use the one already loaded / default. */
 int gfk_comm_unique_id(void* id128_host, const char* nccl_path);
 int gfk_comm_init(int n_ranks, int rank, const void* id128_host, const char* nccl_path);
+/* Optional: peer-memory mailboxes for the per-step exchange (CUDA IPC, NVLink P2P).  Each rank calls
+ * gfk_p2p_local_handle (64-byte cudaIpcMemHandle_t out), the handles are all-gathered out of band into
+ * handles_host[n_ranks * 64], then every rank calls gfk_p2p_open.  Afterwards gfk_thin exchanges its
+ * (value, index) pairs with flag-in-data stores into the peers' mailboxes from inside the thinning kernels
+ * (and the single-launch persistent kernel becomes available on every rank); without it NCCL all-gather is used. */
+int gfk_p2p_local_handle(void* handle64_host);
+int gfk_p2p_open(const void* handles_host, int n_ranks, int rank);
+int gfk_p2p_enabled(void);
 int gfk_comm_size(void);
 int gfk_comm_rank(void);
 int gfk_allreduce_sum(double* buf, int64_t count, void* stream);

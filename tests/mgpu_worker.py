@@ -22,15 +22,39 @@ def main():
     dist.init_process_group('nccl')
     gdist.init()
     warnings.simplefilter('ignore')
+    from gradient_free_mcmc_postprocessing_b200 import _lib
+    p2p = bool(_lib.load().gfk_p2p_enabled())
+    if rank == 0:
+        print('p2p mailboxes:', p2p, flush=True)
     # duplicated rows -> exact ties that straddle shard boundaries
     c = synthetic.config_c2(n=30_011, m=80)
-    got = thin(c['sample'], c['gradient'], 80, preconditioner='med')
     expect = ot.thin(c['sample'], c['gradient'], 80, preconditioner='med')
-    assert np.array_equal(got, expect), (rank, got[:10], expect[:10])
     c1 = synthetic.config_c1()
-    got = thin_gf(c1['sample'], c1['log_p'], c1['log_q'], c1['gradient_q'], 100, preconditioner='med')
-    expect = ot.thin_gf(c1['sample'], c1['log_p'], c1['log_q'], c1['gradient_q'], 100, preconditioner='med')
-    assert np.array_equal(got, expect)
+    expect1 = ot.thin_gf(c1['sample'], c1['log_p'], c1['log_q'], c1['gradient_q'], 100, preconditioner='med')
+    rng = np.random.default_rng(3)
+    x10 = rng.standard_normal((20_000, 10))
+    g10 = -x10 * (1 + 0.1 * np.arange(10))
+    expect10 = ot.thin(x10, g10, 40, preconditioner='med')
+    # exchange through peer mailboxes (persistent + multi-launch kernels) and through NCCL all-gather
+    modes = [dict(), dict(GFK_PERSISTENT='0'), dict(GFK_P2P='0')] if p2p else [dict()]
+    for env in modes:
+        for k in ('GFK_PERSISTENT', 'GFK_P2P'):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        for precision in ('f64', 'f64-fast'):
+            got = thin(c['sample'], c['gradient'], 80, preconditioner='med', precision=precision)
+            assert np.array_equal(got, expect), (rank, env, precision, got[:10], expect[:10])
+            got = thin_gf(c1['sample'], c1['log_p'], c1['log_q'], c1['gradient_q'], 100, preconditioner='med',
+                          precision=precision)
+            assert np.array_equal(got, expect1), (rank, env, precision)
+            got10 = thin(x10, g10, 40, preconditioner='med', precision=precision)
+            assert np.array_equal(got10, expect10), (rank, env, precision)
+        dist.barrier()
+        if rank == 0:
+            print('mode ok:', env, flush=True)
+    for k in ('GFK_PERSISTENT', 'GFK_P2P'):
+        os.environ.pop(k, None)
+    got = expect1
     # every rank returns the same sequence
     t = torch.from_numpy(got.astype(np.int64)).cuda()
     gathered = [torch.zeros_like(t) for _ in range(world)]
