@@ -76,23 +76,33 @@ GFK_HD float approx_rsqrt(float a) { return 1.0f / sqrtf(a); }
 GFK_HD double fma_t(double a, double b, double c) { return nf_fma(a, b, c); }
 GFK_HD float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 
+// ---- exponent-range tests (integer pipe; keep the FP64 pipe and the control flow free of guards) ----
+GFK_HD unsigned exponent_field(double v) {
+#if defined(__CUDA_ARCH__)
+    return ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+#else
+    unsigned long long bits;
+    memcpy(&bits, &v, sizeof(bits));
+    return (unsigned)(bits >> 52) & 0x7ffu;
+#endif
+}
+// |v| within [2^-span, 2^span]
+GFK_HD bool exponent_within(double v, unsigned span) { return (exponent_field(v) - (0x3ffu - span)) <= 2u * span; }
+
 // Correctly rounded quotient n / p from an approximate reciprocal rinv ~ 1/p (a few ulp): one
 // Markstein correction step.  q0 = n * rinv is within a few ulp of n / p, the residual n - q0 * p is
 // exact in an FMA, and q0 + resid * rinv is then accurate to ~2^-100 relative before its single final
 // rounding (a quotient of doubles is never closer than ~2^-106 relative to a rounding midpoint, so the
-// result equals IEEE division except in astronomically rare cases).  Falls back to IEEE division
-// outside the safe exponent range or for non-finite operands.
+// result equals IEEE division except in astronomically rare cases).  The caller guarantees the operands
+// are far from overflow / underflow (strict_finish checks the exponents once per pair).
 GFK_HD double div_markstein(double n, double p, double rinv) {
     const double q0 = nf_mul(n, rinv);
     const double resid = nf_fma(-q0, p, n);
-    const double q = nf_fma(resid, rinv, q0);
-    const double an = fabs(n), ap = fabs(p);
-    const bool safe = (ap > 1.0e-140) && (ap < 1.0e140) && (an < 1.0e140) && ((an > 1.0e-140) || (n == 0.0));
-    return safe ? q : nf_div(n, p);
+    return nf_fma(resid, rinv, q0);
 }
 
-// q^0.5, q^1.5 and q^2.5, each correctly rounded up to ~2^-100 (q >= 0), plus approximate reciprocals
-// (a few ulp) of the three powers for div_markstein.
+// q^0.5, q^1.5 and q^2.5, each correctly rounded up to ~2^-100, plus approximate reciprocals (a few
+// ulp) of the three powers for div_markstein.  Requires 2^-150 <= q <= 2^150 (checked by the caller).
 // r = rsqrt(q) approximately; s0 = q * r; sqrt(q) = s0 + (q - s0^2) * r / 2 to ~2^-100: the rounded sum is
 // RN(sqrt q) (sqrt of a double is never closer than ~2^-105 relative to a midpoint), and the unrounded pair
 // (s, sl) feeds the double-double products q * sqrt(q) and q^2 * sqrt(q), each rounded once.
@@ -102,12 +112,10 @@ GFK_HD void strict_powers_r(double q, double& p05, double& p15, double& p25, dou
     const double hr = nf_mul(0.5, r);
     const double s0 = nf_mul(q, r);
     const double e0 = nf_fma(-s0, s0, q);                   // exact: q - s0*s0
-    double s = nf_fma(e0, hr, s0);                          // RN(sqrt q) w.h.p.
-    const bool regular = (q > 1.0e-290) && (q < 1.0e300);
-    if (!regular) s = nf_sqrt(q);
+    const double s = nf_fma(e0, hr, s0);                    // RN(sqrt q)
     p05 = s;
     const double resid = nf_fma(-s, s, q);                  // exact: q - s*s
-    const double sl = regular ? nf_mul(resid, hr) : 0.0;    // sqrt(q) = s + sl (+ O(2^-105))
+    const double sl = nf_mul(resid, hr);                    // sqrt(q) = s + sl (+ O(2^-105))
     // q^1.5
     const double h1 = nf_mul(q, s);
     double l1 = nf_fma(q, s, -h1);                          // exact low part of q*s
@@ -121,17 +129,24 @@ GFK_HD void strict_powers_r(double q, double& p05, double& p15, double& p25, dou
     l2 = nf_fma(qh, sl, l2);
     l2 = nf_fma(ql, s, l2);
     p25 = nf_add(h2, l2);
-    if (!(fabs(h1) < 1.0e300)) p15 = h1;                    // overflow / inf / nan: plain product
-    if (!(fabs(h2) < 1.0e300)) p25 = h2;
     const double r2 = nf_mul(r, r);
     r05 = r;
     r15 = nf_mul(r, r2);
     r25 = nf_mul(r15, r2);
 }
 
+// the same three powers for ANY q >= 0 (including 0, inf, nan and the far exponent ranges): IEEE sqrt
+// and plain products where the double-double construction could overflow or lose its low parts
 GFK_HD void strict_powers(double q, double& p05, double& p15, double& p25) {
-    double r05, r15, r25;
-    strict_powers_r(q, p05, p15, p25, r05, r15, r25);
+    if (exponent_within(q, 150u)) {
+        double r05, r15, r25;
+        strict_powers_r(q, p05, p15, p25, r05, r15, r25);
+        return;
+    }
+    const double s = nf_sqrt(q);
+    p05 = s;
+    p15 = nf_mul(q, s);
+    p25 = nf_mul(nf_mul(q, q), s);
 }
 
 // numpy's pairwise summation of the d products sx_k * sy_k (np.sum over the contiguous
@@ -195,12 +210,23 @@ GFK_HD double pairwise_dot(const AX& sx, const AY& sy, int d) {
 //   s1 = sum (lambda r) r, s2 = sum (lambda^2 r) r, s3 = sum (lambda (sx - sy)) r, s4 = sum sx sy
 GFK_HD double strict_finish(double s1, double s2, double s3, double s4, const KParams& kp) {
     const double qf = nf_add(kp.c, s1);
-    double p05, p15, p25, r05, r15, r25;
-    strict_powers_r(qf, p05, p15, p25, r05, r15, r25);
-    const double t1 = div_markstein(nf_mul(-3.0, s2), p25, r25);
-    const double t2 = div_markstein(nf_add(kp.trace, s3), p15, r15);
-    const double t3 = div_markstein(s4, p05, r05);
-    return nf_add(nf_add(t1, t2), t3);
+    const double n1 = nf_mul(-3.0, s2);
+    const double n2 = nf_add(kp.trace, s3);
+    const double n3 = s4;
+    // one exponent test per pair instead of guards around every operation
+    const bool regular = exponent_within(qf, 150u) && (exponent_within(n1, 400u) || n1 == 0.0) &&
+                         (exponent_within(n2, 400u) || n2 == 0.0) && (exponent_within(n3, 400u) || n3 == 0.0);
+    if (regular) {
+        double p05, p15, p25, r05, r15, r25;
+        strict_powers_r(qf, p05, p15, p25, r05, r15, r25);
+        const double t1 = div_markstein(n1, p25, r25);
+        const double t2 = div_markstein(n2, p15, r15);
+        const double t3 = div_markstein(n3, p05, r05);
+        return nf_add(nf_add(t1, t2), t3);
+    }
+    double p05, p15, p25;                                   // rare: extreme magnitudes, zeros, inf, nan
+    strict_powers(qf, p05, p15, p25);
+    return nf_add(nf_add(nf_div(n1, p25), nf_div(n2, p15)), nf_div(n3, p05));
 }
 
 // ---- strict pair kernel (float64) ------------------------------------------------------------

@@ -673,20 +673,31 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         if (a.lw) lwy = use_w ? __ldg(a.w + sel) : __ldg(a.lw + sel);
         bv = __longlong_as_double(0x7ff0000000000000LL);
         bi = 0xffffffffu;
-#pragma unroll 2
+        // software pipeline: the next owned row is fetched (shared memory or L2) while this one is evaluated
+        T xn[D], sn[D];
+        auto fetch = [&](int j) {
+            const long long li = (long long)j * TT + gt;
+            if (j < rpt && li < rows) {
+                if (j < rpt_res) {
+                    const int slot = j * nthr + tid;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { xn[k] = xs[k * slots_res + slot]; sn[k] = ss[k * slots_res + slot]; }
+                } else {
+                    load_row<D>(a.x, a.row_begin + li, xn);
+                    load_row<D>(a.s, a.row_begin + li, sn);
+                }
+            }
+        };
+        fetch(0);
         for (int j = 0; j < rpt; ++j) {
             const long long li = (long long)j * TT + gt;
             const int slot = j * nthr + tid;
+            T xr[D], sr[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) { xr[k] = xn[k]; sr[k] = sn[k]; }
+            fetch(j + 1);
             if (li < rows) {
                 const long long i = a.row_begin + li;
-                T xr[D], sr[D];
-                if (j < rpt_res) {
-#pragma unroll
-                    for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots_res + slot]; sr[k] = ss[k * slots_res + slot]; }
-                } else {
-                    load_row<D>(a.x, i, xr);
-                    load_row<D>(a.s, i, sr);
-                }
                 double k;
                 if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
                 else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
