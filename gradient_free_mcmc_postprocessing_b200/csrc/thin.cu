@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
 // -> every CTA reduces the <= 148 partials itself (no second barrier) -> next selected row.
 constexpr int kPersistThreads = 512;
 
-template <typename T, int D, bool STRICT>
+template <typename T, int D, bool STRICT, bool PREFETCH>
 __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double sv[32];
@@ -673,6 +673,42 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         if (a.lw) lwy = use_w ? __ldg(a.w + sel) : __ldg(a.lw + sel);
         bv = __longlong_as_double(0x7ff0000000000000LL);
         bi = 0xffffffffu;
+        if constexpr (!PREFETCH) {
+#pragma unroll 2
+        for (int j = 0; j < rpt; ++j) {
+            const long long li = (long long)j * TT + gt;
+            const int slot = j * nthr + tid;
+            if (li < rows) {
+                const long long i = a.row_begin + li;
+                T xr[D], sr[D];
+                if (j < rpt_res) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots_res + slot]; sr[k] = ss[k * slots_res + slot]; }
+                } else {
+                    load_row<D>(a.x, i, xr);
+                    load_row<D>(a.s, i, sr);
+                }
+                double k;
+                if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
+                else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
+                double v;
+                const double av = A_sh[slot];
+                if constexpr (STRICT) {
+                    if (a.lw) k = __dmul_rn(exp((double)lw_sh[slot] + (double)lwy), k);
+                    v = __dadd_rn(av, __dmul_rn(2.0, k));
+                } else {
+                    if (a.lw) {
+                        const double wgt = use_w ? (double)(lw_sh[slot] * lwy) : exp((double)lw_sh[slot] + (double)lwy);
+                        v = fma(2.0 * wgt, k, av);
+                    } else {
+                        v = fma(2.0, k, av);
+                    }
+                }
+                A_sh[slot] = v;
+                if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
+            }
+        }
+        } else {
         // software pipeline: the next owned row is fetched (shared memory or L2) while this one is evaluated
         T xn[D], sn[D];
         auto fetch = [&](int j) {
@@ -717,6 +753,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 A_sh[slot] = v;
                 if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
             }
+        }
         }
     }
     // ---- write the running objective back -----------------------------------------------------------
@@ -815,7 +852,10 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
     ThinArgs<T> args = a;
     int m_arg = m, rpt_arg = rpt, res_arg = rpt_res;
     void* params[] = {&args, &m_arg, &rpt_arg, &res_arg};
-    const void* fn = (const void*)thin_persistent_kernel<T, D, STRICT>;
+    const char* lenv = getenv("GFK_PREFETCH");
+    const bool prefetch = lenv && lenv[0] == '1';
+    const void* fn = prefetch ? (const void*)thin_persistent_kernel<T, D, STRICT, true>
+                              : (const void*)thin_persistent_kernel<T, D, STRICT, false>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;

@@ -92,3 +92,29 @@ def test_synthetic_configs_shapes():
     c2 = synthetic.config_c2(n=5000)
     assert c2['sample'].shape == (5000, 4)
     assert len(np.unique(c2['sample'], axis=0)) < 2500           # MCMC-like duplicated rows
+
+
+def test_install_as_stein_thinning_aliases():
+    import sys
+    import gradient_free_mcmc_postprocessing_b200 as pkg
+    saved = {k: sys.modules.get(k) for k in ('stein_thinning', 'stein_thinning.thinning', 'stein_thinning.kernel',
+                                             'stein_thinning.stein')}
+    try:
+        pkg.install_as_stein_thinning()
+        from stein_thinning.kernel import make_imq, make_precon, vfk0_imq  # noqa: F401
+        from stein_thinning.stein import kmat as k2, ksd as s2  # noqa: F401
+        from stein_thinning.thinning import (_greedy_search, _make_stein_gf_integrand, _make_stein_integrand,  # noqa: F401
+                                             _validate_and_standardize, thin as t2, thin_gf)  # noqa: F401
+        import inspect
+        assert list(inspect.signature(thin_gf).parameters)[:8] == [
+            'sample', 'log_p', 'log_q', 'gradient_q', 'n_points', 'standardize', 'preconditioner', 'range_cap']
+        assert list(inspect.signature(t2).parameters)[:5] == ['sample', 'gradient', 'n_points', 'standardize',
+                                                               'preconditioner']
+        assert inspect.signature(t2).parameters['preconditioner'].default == 'id'
+        assert inspect.signature(thin_gf).parameters['range_cap'].default is None
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -51,11 +51,11 @@ def timed(fn, reps=3):
 
 warnings.simplefilter('ignore')
 timings = {}
-variants = [('persist', {}), ('persist768', {'GFK_PTHREADS': '768'}), ('multilaunch', {'GFK_PERSISTENT': '0'})]
+variants = [('persist', {}), ('persist-prefetch', {'GFK_PREFETCH': '1'}), ('multilaunch', {'GFK_PERSISTENT': '0'})]
 for cname, var in [(c, v) for c in ('c1', 'c2', 'c3', 'c5') for v in variants]:
     if cname == 'c5' and var[0] != 'multilaunch':
         continue
-    for k in ('GFK_RESIDENT', 'GFK_PERSISTENT', 'GFK_PTHREADS'):
+    for k in ('GFK_RESIDENT', 'GFK_PERSISTENT', 'GFK_PREFETCH'):
         os.environ.pop(k, None)
     os.environ.update(var[1])
     c = synthetic.CONFIGS[cname]()
@@ -76,7 +76,7 @@ for cname, var in [(c, v) for c in ('c1', 'c2', 'c3', 'c5') for v in variants]:
         print(key, timings[key], flush=True)
         del p
 out['thin'] = timings
-for k in ('GFK_RESIDENT', 'GFK_PERSISTENT', 'GFK_PTHREADS'):
+for k in ('GFK_RESIDENT', 'GFK_PERSISTENT', 'GFK_PREFETCH'):
     os.environ.pop(k, None)
 c = synthetic.config_c4(n=50_000)
 for prec in ('f64-fast', 'f32'):
