@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgfk.so')
+LIB_PATH = os.environ.get('GFK_LIB') or os.path.join(_HERE, 'libgfk.so')   # GFK_LIB: A/B builds only
 
 GFK_OK = 0
 GFK_EINVAL, GFK_ECUDA, GFK_ENCCL, GFK_EUNSUPPORTED, GFK_ENUMERIC = 1, 2, 3, 4, 5
@@ -86,6 +86,8 @@ def load():
             'There is no CPU fallback.')
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in PROTOTYPES.items():
+        if not hasattr(lib, name) and os.environ.get('GFK_LIB'):
+            continue                  # A/B runs against an older build
         fn = getattr(lib, name)       # AttributeError if the build is stale
         fn.restype = restype
         fn.argtypes = argtypes

@@ -45,7 +45,20 @@ __device__ __forceinline__ long long row_of(const KsdArgs<T>& a, long long t) {
     return a.sel ? (long long)a.sel[t] : t;
 }
 
-// stage dimensions [k0, k0 + kc) of rows [t0, t0 + TILE) into dst[k][LD] (zero padded).
+// ---- asynchronous global -> shared copies (LDGSTS): no register staging, overlap with the FMA loop ----
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
+}
+__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// stage dimensions [k0, k0 + kc) of rows [t0, t0 + TILE) into dst[k][LD] (zero padded), asynchronously.
 // Consecutive threads read consecutive k of one row (coalesced); the padded LD spreads the stores.
 template <typename T, int KC>
 __device__ __forceinline__ void stage_tile(const KsdArgs<T>& a, const T* __restrict__ src, long long t0, int k0,
@@ -54,24 +67,22 @@ __device__ __forceinline__ void stage_tile(const KsdArgs<T>& a, const T* __restr
     for (int e = threadIdx.x; e < TILE * KC; e += KSD_THREADS) {
         const int r = e / KC, k = e - r * KC;
         const long long t = t0 + r;
-        T v = T(0);
-        if (k < kc && t < a.m) v = __ldg(src + row_of(a, t) * d + k0 + k);
-        dst[k * LD + r] = v;
+        if (k < kc && t < a.m) cp_async_elem(dst + k * LD + r, src + row_of(a, t) * d + k0 + k);
+        else dst[k * LD + r] = T(0);
     }
 }
 
-// dynamic shared memory: xr sr xc sc [xlr xlc] each KC x LD, then wr[TILE] wc[TILE]
+// dynamic shared memory: 2 stage buffers, each { xr sr xc sc [xlr xlc] } of KC x LD, then wr[TILE], wc[2][TILE].
+// Stages are the (column tile J, dimension chunk k0) pairs in order; stage s+1 is copied in with cp.async
+// while stage s is consumed.  With d <= KC the row tile is invariant and staged once into buffer 0's row slots.
 template <typename T, bool DENSE, int KC>
 __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
     extern __shared__ __align__(16) unsigned char ksd_smem[];
-    T* xr = reinterpret_cast<T*>(ksd_smem);
-    T* sr = xr + KC * LD;
-    T* xc = sr + KC * LD;
-    T* sc = xc + KC * LD;
-    T* xlr = sc + KC * LD;
-    T* xlc = xlr + (DENSE ? KC * LD : 0);
-    T* wr = xlc + (DENSE ? KC * LD : 0);
-    T* wc = wr + TILE;
+    constexpr int NARR = DENSE ? 6 : 4;
+    T* buf0 = reinterpret_cast<T*>(ksd_smem);
+    T* buf1 = buf0 + NARR * KC * LD;
+    T* wr = buf1 + NARR * KC * LD;
+    T* wcb = wr + TILE;                       // wc[2][TILE]
 
     const long long ntiles = (a.m + TILE - 1) / TILE;
     // this rank's tiles, largest (most column tiles) first
@@ -84,6 +95,31 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
     const bool gf = (a.lw != nullptr);
     const bool pre_w = (a.w != nullptr);
     const bool single_chunk = (d <= KC);
+    const int nchunks = (d + KC - 1) / KC;
+    const long long nstages = (I + 1) * nchunks;
+
+    auto issue = [&](long long stage) {
+        T* base = (stage & 1) ? buf1 : buf0;
+        const long long J = stage / nchunks;
+        const int k0 = (int)(stage - J * nchunks) * KC;
+        const int kc = min(KC, d - k0);
+        const long long c0 = J * TILE;
+        if (!single_chunk) {
+            stage_tile<T, KC>(a, a.x, t0, k0, kc, base);
+            stage_tile<T, KC>(a, a.s, t0, k0, kc, base + KC * LD);
+            if (DENSE) stage_tile<T, KC>(a, a.xl, t0, k0, kc, base + 4 * KC * LD);
+        }
+        stage_tile<T, KC>(a, a.x, c0, k0, kc, base + 2 * KC * LD);
+        stage_tile<T, KC>(a, a.s, c0, k0, kc, base + 3 * KC * LD);
+        if (DENSE) stage_tile<T, KC>(a, a.xl, c0, k0, kc, base + 5 * KC * LD);
+        if (k0 == 0 && threadIdx.x < TILE) {
+            const long long t = c0 + threadIdx.x;
+            T v = T(0);
+            if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
+            wcb[(J & 1) * TILE + threadIdx.x] = v;
+        }
+        cp_async_commit();
+    };
 
     if (threadIdx.x < TILE) {
         const long long t = t0 + threadIdx.x;
@@ -91,99 +127,99 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
         if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
         wr[threadIdx.x] = v;
     }
-    if (single_chunk) {   // the row tile is invariant over J: stage it once
-        stage_tile<T, KC>(a, a.x, t0, 0, d, xr);
-        stage_tile<T, KC>(a, a.s, t0, 0, d, sr);
-        if (DENSE) stage_tile<T, KC>(a, a.xl, t0, 0, d, xlr);
+    if (single_chunk) {   // the row tile is invariant over J: stage it once (buffer 0's row slots)
+        stage_tile<T, KC>(a, a.x, t0, 0, d, buf0);
+        stage_tile<T, KC>(a, a.s, t0, 0, d, buf0 + KC * LD);
+        if (DENSE) stage_tile<T, KC>(a, a.xl, t0, 0, d, buf0 + 4 * KC * LD);
     }
+    issue(0);
+
     double rowacc[MT];
 #pragma unroll
     for (int i = 0; i < MT; ++i) rowacc[i] = 0.0;
+    T rr[MT][MT], su[MT][MT], ss[MT][MT], uu[DENSE ? MT : 1][DENSE ? MT : 1];
 
-    for (long long J = 0; J <= I; ++J) {
+    for (long long stage = 0; stage < nstages; ++stage) {
+        const long long J = stage / nchunks;
+        const int chunk = (int)(stage - J * nchunks);
+        const int kc = min(KC, d - chunk * KC);
         const long long c0 = J * TILE;
-        T rr[MT][MT], su[MT][MT], ss[MT][MT], uu[DENSE ? MT : 1][DENSE ? MT : 1];
+        if (stage + 1 < nstages) {
+            issue(stage + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        T* base = (stage & 1) ? buf1 : buf0;
+        const T* xr = single_chunk ? buf0 : base;
+        const T* sr = single_chunk ? buf0 + KC * LD : base + KC * LD;
+        const T* xlr = single_chunk ? buf0 + 4 * KC * LD : base + 4 * KC * LD;
+        const T* xc = base + 2 * KC * LD;
+        const T* sc = base + 3 * KC * LD;
+        const T* xlc = base + 5 * KC * LD;
+        if (chunk == 0) {
 #pragma unroll
-        for (int i = 0; i < MT; ++i)
+            for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                rr[i][j] = T(0); su[i][j] = T(0); ss[i][j] = T(0);
-                if (DENSE) uu[i][j] = T(0);
-            }
-        for (int k0 = 0; k0 < d; k0 += KC) {
-            const int kc = min(KC, d - k0);
-            __syncthreads();   // previous chunk / tile fully consumed
-            if (!single_chunk) {
-                stage_tile<T, KC>(a, a.x, t0, k0, kc, xr);
-                stage_tile<T, KC>(a, a.s, t0, k0, kc, sr);
-                if (DENSE) stage_tile<T, KC>(a, a.xl, t0, k0, kc, xlr);
-            }
-            stage_tile<T, KC>(a, a.x, c0, k0, kc, xc);
-            stage_tile<T, KC>(a, a.s, c0, k0, kc, sc);
-            if (DENSE) stage_tile<T, KC>(a, a.xl, c0, k0, kc, xlc);
-            if (k0 == 0 && threadIdx.x < TILE) {
-                const long long t = c0 + threadIdx.x;
-                T v = T(0);
-                if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
-                wc[threadIdx.x] = v;
-            }
-            __syncthreads();
+                for (int j = 0; j < MT; ++j) {
+                    rr[i][j] = T(0); su[i][j] = T(0); ss[i][j] = T(0);
+                    if (DENSE) uu[i][j] = T(0);
+                }
+        }
 #pragma unroll 2
-            for (int k = 0; k < kc; ++k) {
-                T xi[MT], si[MT], xj[MT], sj[MT], li[DENSE ? MT : 1], lj[DENSE ? MT : 1];
+        for (int k = 0; k < kc; ++k) {
+            T xi[MT], si[MT], xj[MT], sj[MT], li[DENSE ? MT : 1], lj[DENSE ? MT : 1];
 #pragma unroll
-                for (int i = 0; i < MT; ++i) {
-                    xi[i] = xr[k * LD + ty * MT + i];
-                    si[i] = sr[k * LD + ty * MT + i];
-                    xj[i] = xc[k * LD + tx * MT + i];
-                    sj[i] = sc[k * LD + tx * MT + i];
+            for (int i = 0; i < MT; ++i) {
+                xi[i] = xr[k * LD + ty * MT + i];
+                si[i] = sr[k * LD + ty * MT + i];
+                xj[i] = xc[k * LD + tx * MT + i];
+                sj[i] = sc[k * LD + tx * MT + i];
+                if (DENSE) {
+                    li[i] = xlr[k * LD + ty * MT + i];
+                    lj[i] = xlc[k * LD + tx * MT + i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                    const T r = xi[i] - xj[j];
+                    const T ds = si[i] - sj[j];
                     if (DENSE) {
-                        li[i] = xlr[k * LD + ty * MT + i];
-                        lj[i] = xlc[k * LD + tx * MT + i];
+                        const T u = li[i] - lj[j];
+                        rr[i][j] = fma_t(u, r, rr[i][j]);
+                        uu[i][j] = fma_t(u, u, uu[i][j]);
+                        su[i][j] = fma_t(ds, u, su[i][j]);
+                    } else {
+                        rr[i][j] = fma_t(r, r, rr[i][j]);
+                        su[i][j] = fma_t(ds, r, su[i][j]);
                     }
+                    ss[i][j] = fma_t(si[i], sj[j], ss[i][j]);
                 }
+        }
+        if (chunk == nchunks - 1) {
+            // epilogue of column tile J: powers, weights, triangular mask
+            const T* wc = wcb + (J & 1) * TILE;
 #pragma unroll
-                for (int i = 0; i < MT; ++i)
+            for (int i = 0; i < MT; ++i) {
+                const long long t = t0 + ty * MT + i;
+                double part_sum = 0.0;
 #pragma unroll
-                    for (int j = 0; j < MT; ++j) {
-                        const T r = xi[i] - xj[j];
-                        const T ds = si[i] - sj[j];
-                        if (DENSE) {
-                            const T u = li[i] - lj[j];
-                            rr[i][j] = fma_t(u, r, rr[i][j]);
-                            uu[i][j] = fma_t(u, u, uu[i][j]);
-                            su[i][j] = fma_t(ds, u, su[i][j]);
-                        } else {
-                            rr[i][j] = fma_t(r, r, rr[i][j]);
-                            su[i][j] = fma_t(ds, r, su[i][j]);
-                        }
-                        ss[i][j] = fma_t(si[i], sj[j], ss[i][j]);
+                for (int j = 0; j < MT; ++j) {
+                    const long long b = c0 + tx * MT + j;
+                    T kv = fast_finish<T, DENSE>(rr[i][j], DENSE ? uu[i][j] : T(0), su[i][j], ss[i][j], a.kp);
+                    if (gf) {
+                        const T wi = wr[ty * MT + i], wj = wc[tx * MT + j];
+                        kv *= pre_w ? (wi * wj) : (T)exp((double)wi + (double)wj);
                     }
+                    if (b < t && t < a.m) part_sum += (double)kv;
+                }
+                rowacc[i] += part_sum;
             }
         }
-        // epilogue: powers, weights, triangular mask
-        const T lam = T(a.kp.lambda);
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            const long long t = t0 + ty * MT + i;
-            double part_sum = 0.0;
-#pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                const long long b = c0 + tx * MT + j;
-                const T qf = DENSE ? (T(a.kp.c) + rr[i][j]) : fma_t(lam, rr[i][j], T(a.kp.c));
-                const T n1 = DENSE ? (T(-3) * uu[i][j]) : (T(-3) * T(a.kp.lambda_sq) * rr[i][j]);
-                const T n2 = DENSE ? (T(a.kp.trace) + su[i][j]) : fma_t(lam, su[i][j], T(a.kp.trace));
-                const T i1 = approx_rsqrt(qf);
-                const T i2 = i1 * i1, i3 = i1 * i2, i5 = i3 * i2;
-                T kv = fma_t(n1, i5, fma_t(n2, i3, ss[i][j] * i1));
-                if (gf) {
-                    const T wi = wr[ty * MT + i], wj = wc[tx * MT + j];
-                    kv *= pre_w ? (wi * wj) : (T)exp((double)wi + (double)wj);
-                }
-                if (b < t && t < a.m) part_sum += (double)kv;
-            }
-            rowacc[i] += part_sum;
-        }
+        __syncthreads();   // buffer (stage & 1) is free for the copy issued at the top of the next iteration
     }
     // reduce the TILE/MT threads that share a row (consecutive lanes: tx = lane % 16)
 #pragma unroll
@@ -330,13 +366,13 @@ static int rowsums_typed(const gfk_problem* p, const uint32_t* sel, int64_t m, i
     if (my_tiles > 0) {
         if (p->xl) {
             constexpr int KC = 16;
-            const size_t smem = sizeof(T) * (size_t)(6 * KC * LD + 2 * TILE);
+            const size_t smem = sizeof(T) * (size_t)(2 * 6 * KC * LD + 3 * TILE);
             GFK_CUDA(cudaFuncSetAttribute(ksd_rowsum_kernel<T, true, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
             ksd_rowsum_kernel<T, true, KC><<<(unsigned)my_tiles, KSD_THREADS, smem, st>>>(a);
         } else {
             constexpr int KC = 32;
-            const size_t smem = sizeof(T) * (size_t)(4 * KC * LD + 2 * TILE);
+            const size_t smem = sizeof(T) * (size_t)(2 * 4 * KC * LD + 3 * TILE);
             GFK_CUDA(cudaFuncSetAttribute(ksd_rowsum_kernel<T, false, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
             ksd_rowsum_kernel<T, false, KC><<<(unsigned)my_tiles, KSD_THREADS, smem, st>>>(a);

@@ -24,8 +24,10 @@
 
 #if defined(__CUDACC__)
 #define GFK_HD __host__ __device__ __forceinline__
+#define GFK_HD_COLD static __host__ __device__ __noinline__   // rare paths: kept out of the hot loops' instruction footprint
 #else
 #define GFK_HD inline
+#define GFK_HD_COLD inline
 #endif
 
 namespace gfk {
@@ -206,6 +208,13 @@ GFK_HD double pairwise_dot(const AX& sx, const AY& sy, int d) {
     return nf_add(0.0, ret);
 }
 
+// out-of-line: IEEE sqrt / division, valid for any operands
+GFK_HD_COLD double strict_finish_rare(double qf, double n1, double n2, double n3) {
+    double p05, p15, p25;
+    strict_powers(qf, p05, p15, p25);
+    return nf_add(nf_add(nf_div(n1, p25), nf_div(n2, p15)), nf_div(n3, p05));
+}
+
 // From the four sums to the kernel value, numpy's order:
 //   s1 = sum (lambda r) r, s2 = sum (lambda^2 r) r, s3 = sum (lambda (sx - sy)) r, s4 = sum sx sy
 GFK_HD double strict_finish(double s1, double s2, double s3, double s4, const KParams& kp) {
@@ -224,9 +233,7 @@ GFK_HD double strict_finish(double s1, double s2, double s3, double s4, const KP
         const double t3 = div_markstein(n3, p05, r05);
         return nf_add(nf_add(t1, t2), t3);
     }
-    double p05, p15, p25;                                   // rare: extreme magnitudes, zeros, inf, nan
-    strict_powers(qf, p05, p15, p25);
-    return nf_add(nf_add(nf_div(n1, p25), nf_div(n2, p15)), nf_div(n3, p05));
+    return strict_finish_rare(qf, n1, n2, n3);              // extreme magnitudes, zeros, inf, nan
 }
 
 // ---- strict pair kernel (float64) ------------------------------------------------------------

@@ -33,6 +33,7 @@ struct __align__(16) ThinWs {
     // persistent kernel, flag-in-data slots: every 8-byte word carries (tag << 32 | payload), so a reader
     // that sees the expected tag in all three words has the whole record - no fences, no atomics
     unsigned long long ll[2][kMaxBlocks / 2][4];
+    MailArgs mail;           // peer mailboxes of this job (written by thin_reset_kernel)
 };
 
 template <typename T>
@@ -49,7 +50,7 @@ struct ThinArgs {
     uint32_t* idx_out;
     int n_ranks;
     int step;        // multi-launch kernels: index of the exchange this launch produces (consumes step - 1)
-    MailArgs mail;   // peer mailboxes (enabled: exchange through them instead of NCCL)
+    int mail_enabled; // exchange through the peer mailboxes in ws->mail instead of NCCL
 };
 
 // ---- row access -------------------------------------------------------------------------------
@@ -139,6 +140,7 @@ __device__ __forceinline__ Cand mail_wait(const MailArgs& m, int n_ranks, int ex
         const volatile unsigned long long* w = m.local + mail_offset(m, exchange, lane);
         unsigned long long w0, w1, w2;
         unsigned spins = 0;
+#pragma unroll 1
         for (;;) {
             w0 = w[0]; w1 = w[1]; w2 = w[2];
             if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && (unsigned)(w2 >> 32) == tag) break;
@@ -155,14 +157,22 @@ __device__ __forceinline__ Cand mail_wait(const MailArgs& m, int n_ranks, int ex
     return c;
 }
 
+// post + wait as one out-of-line call: keeps the single-GPU step loop of the persistent kernel small enough
+// for the instruction cache (one warp walks this code once per step, so every cold line is exposed latency)
+__device__ __noinline__ Cand mail_exchange(const MailArgs& m, int n_ranks, int exchange, double v, unsigned i,
+                                            int lane, bool post, bool& dead, const unsigned* abort_flag) {
+    if (post) mail_post(m, n_ranks, exchange, v, i, lane);
+    return mail_wait(m, n_ranks, exchange, lane, dead, abort_flag);
+}
+
 // winner of exchange (a.step - 1): from the peer mailboxes (warp 0 polls, block broadcast) or from recv[]
 template <typename T>
 __device__ __forceinline__ Cand pick_winner(const ThinArgs<T>& a) {
-    if (a.mail.enabled && a.n_ranks > 1) {
+    if (a.mail_enabled && a.n_ranks > 1) {
         __shared__ Cand win_bc;
         if (threadIdx.x < 32) {
             bool dead;
-            const Cand c = mail_wait(a.mail, a.n_ranks, a.step - 1, threadIdx.x, dead, nullptr);
+            const Cand c = mail_wait(a.ws->mail, a.n_ranks, a.step - 1, threadIdx.x, dead, nullptr);
             if (threadIdx.x == 0) win_bc = c;
         }
         __syncthreads();
@@ -205,7 +215,7 @@ __device__ __forceinline__ void grid_argmin_publish(double v, unsigned i, const 
     }
     __syncthreads();
     block_argmin(bv, bi, sv, si);      // every lane of warp 0 holds the result
-    if (a.mail.enabled && n_ranks > 1 && threadIdx.x < 32) mail_post(a.mail, n_ranks, a.step, bv, bi, threadIdx.x);
+    if (a.mail_enabled && n_ranks > 1 && threadIdx.x < 32) mail_post(ws->mail, n_ranks, a.step, bv, bi, threadIdx.x);
     if (threadIdx.x == 0) {
         ws->send.v = bv;
         ws->send.i = bi;
@@ -550,7 +560,7 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
 // -> every CTA reduces the <= 148 partials itself (no second barrier) -> next selected row.
 constexpr int kPersistThreads = 512;
 
-template <typename T, int D, bool STRICT, bool PREFETCH>
+template <typename T, int D, bool STRICT, bool MULTI>
 __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double sv[32];
@@ -627,10 +637,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 double wv = __longlong_as_double(0x7ff0000000000000LL);
                 unsigned wi = 0xffffffffu;
                 bool dead = false;
+#pragma unroll 1
                 for (unsigned b = tid; b < gridDim.x && !dead; b += 32) {
                     const volatile unsigned long long* w = slots_ll[b];
                     unsigned long long w0, w1, w2;
                     unsigned spins = 0;
+#pragma unroll 1
                     for (;;) {
                         w0 = w[0]; w1 = w[1]; w2 = w[2];
                         if ((w0 >> 32) == (tag >> 32) && (w1 >> 32) == (tag >> 32) && (w2 >> 32) == (tag >> 32)) break;
@@ -642,11 +654,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 }
                 dead = __any_sync(0xffffffffu, dead);
                 warp_argmin(wv, wi);
-                if (a.n_ranks > 1 && !dead) {
+                if (MULTI && !dead) {
                     // cross-GPU stage: CTA 0 stores this rank's winner into every peer's mailbox over NVLink;
                     // every CTA polls the local mailbox for all ranks' winners and reduces them
-                    if (blockIdx.x == 0) mail_post(a.mail, a.n_ranks, step, wv, wi, tid);
-                    const Cand g = mail_wait(a.mail, a.n_ranks, step, tid, dead, &ws->abort);
+                    const Cand g = mail_exchange(ws->mail, a.n_ranks, step, wv, wi, tid, blockIdx.x == 0, dead, &ws->abort);
                     wv = g.v;
                     wi = g.i;
                 }
@@ -673,7 +684,6 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         if (a.lw) lwy = use_w ? __ldg(a.w + sel) : __ldg(a.lw + sel);
         bv = __longlong_as_double(0x7ff0000000000000LL);
         bi = 0xffffffffu;
-        if constexpr (!PREFETCH) {
 #pragma unroll 2
         for (int j = 0; j < rpt; ++j) {
             const long long li = (long long)j * TT + gt;
@@ -708,53 +718,6 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
             }
         }
-        } else {
-        // software pipeline: the next owned row is fetched (shared memory or L2) while this one is evaluated
-        T xn[D], sn[D];
-        auto fetch = [&](int j) {
-            const long long li = (long long)j * TT + gt;
-            if (j < rpt && li < rows) {
-                if (j < rpt_res) {
-                    const int slot = j * nthr + tid;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) { xn[k] = xs[k * slots_res + slot]; sn[k] = ss[k * slots_res + slot]; }
-                } else {
-                    load_row<D>(a.x, a.row_begin + li, xn);
-                    load_row<D>(a.s, a.row_begin + li, sn);
-                }
-            }
-        };
-        fetch(0);
-        for (int j = 0; j < rpt; ++j) {
-            const long long li = (long long)j * TT + gt;
-            const int slot = j * nthr + tid;
-            T xr[D], sr[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) { xr[k] = xn[k]; sr[k] = sn[k]; }
-            fetch(j + 1);
-            if (li < rows) {
-                const long long i = a.row_begin + li;
-                double k;
-                if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
-                else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
-                double v;
-                const double av = A_sh[slot];
-                if constexpr (STRICT) {
-                    if (a.lw) k = __dmul_rn(exp((double)lw_sh[slot] + (double)lwy), k);
-                    v = __dadd_rn(av, __dmul_rn(2.0, k));
-                } else {
-                    if (a.lw) {
-                        const double wgt = use_w ? (double)(lw_sh[slot] * lwy) : exp((double)lw_sh[slot] + (double)lwy);
-                        v = fma(2.0 * wgt, k, av);
-                    } else {
-                        v = fma(2.0, k, av);
-                    }
-                }
-                A_sh[slot] = v;
-                if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
-            }
-        }
-        }
     }
     // ---- write the running objective back -----------------------------------------------------------
     for (int j = 0; j < rpt; ++j) {
@@ -773,11 +736,12 @@ __global__ void thin_finish_kernel(ThinArgs<T> a) {
     }
 }
 
-__global__ void thin_reset_kernel(ThinWs* ws) {
+__global__ void thin_reset_kernel(ThinWs* ws, MailArgs mail) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ws->counter = 0;
         ws->step = 0;
         ws->abort = 0;
+        ws->mail = mail;
     }
     unsigned long long* ll = &ws->ll[0][0][0];
     for (int e = threadIdx.x; e < 2 * (kMaxBlocks / 2) * 4; e += blockDim.x) ll[e] = 0ull;
@@ -824,7 +788,7 @@ static int launch_step(const ThinArgs<T>& a, int d, cudaStream_t st, int grid_sm
 
 // persistent path: returns 1 if it ran, 0 if not eligible, < 0 on error
 template <typename T, int D, bool STRICT>
-static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
+static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, cudaStream_t st) {
     const long long rows = a.row_end - a.row_begin;
     int dev = 0, coop = 0, smem_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -852,10 +816,8 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
     ThinArgs<T> args = a;
     int m_arg = m, rpt_arg = rpt, res_arg = rpt_res;
     void* params[] = {&args, &m_arg, &rpt_arg, &res_arg};
-    const char* lenv = getenv("GFK_PREFETCH");
-    const bool prefetch = lenv && lenv[0] == '1';
-    const void* fn = prefetch ? (const void*)thin_persistent_kernel<T, D, STRICT, true>
-                              : (const void*)thin_persistent_kernel<T, D, STRICT, false>;
+    const void* fn = (a.n_ranks > 1) ? (const void*)thin_persistent_kernel<T, D, STRICT, true>
+                                     : (const void*)thin_persistent_kernel<T, D, STRICT, false>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -865,7 +827,7 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
         cudaGetLastError();
         return 0;
     }
-    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws);
+    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail);
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(threads), params, smem, st);
     if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
     count_launches(2);
@@ -873,15 +835,15 @@ static int try_persistent_d(const ThinArgs<T>& a, int m, cudaStream_t st) {
 }
 
 template <typename T, bool STRICT>
-static int try_persistent(const ThinArgs<T>& a, int d, int m, cudaStream_t st) {
+static int try_persistent(const ThinArgs<T>& a, const MailArgs& mail, int d, int m, cudaStream_t st) {
     const char* env = getenv("GFK_PERSISTENT");
     if (env && env[0] == '0') return 0;
-    if ((a.n_ranks != 1 && !a.mail.enabled) || a.xl != nullptr) return 0;
+    if ((a.n_ranks != 1 && !a.mail_enabled) || a.xl != nullptr) return 0;
     switch (d) {
-        case 1: return try_persistent_d<T, 1, STRICT>(a, m, st);
-        case 2: return try_persistent_d<T, 2, STRICT>(a, m, st);
-        case 3: return try_persistent_d<T, 3, STRICT>(a, m, st);
-        case 4: return try_persistent_d<T, 4, STRICT>(a, m, st);
+        case 1: return try_persistent_d<T, 1, STRICT>(a, mail, m, st);
+        case 2: return try_persistent_d<T, 2, STRICT>(a, mail, m, st);
+        case 3: return try_persistent_d<T, 3, STRICT>(a, mail, m, st);
+        case 4: return try_persistent_d<T, 4, STRICT>(a, mail, m, st);
         default: return 0;
     }
 }
@@ -903,11 +865,13 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     a.idx_out = idx_out;
     a.n_ranks = comm_size();
     a.step = 0;
-    p2p_next_job(&a.mail, m);
-    if (a.n_ranks == 1) a.mail.enabled = 0;
+    MailArgs mail;
+    p2p_next_job(&mail, m);
+    if (a.n_ranks == 1) mail.enabled = 0;
     if (const char* penv = getenv("GFK_P2P")) {
-        if (penv[0] == '0') a.mail.enabled = 0;      // force the NCCL exchange (A/B measurements)
+        if (penv[0] == '0') mail.enabled = 0;        // force the NCCL exchange (A/B measurements)
     }
+    a.mail_enabled = mail.enabled;
     const int d = p->d;
     const long long rows = row_end - row_begin;
     const int sms = sm_count();
@@ -939,7 +903,7 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
         return (int)blocks;
     };
     {
-        const int pr = try_persistent<T, STRICT>(a, d, m, st);
+        const int pr = try_persistent<T, STRICT>(a, mail, d, m, st);
         if (pr < 0) return -pr;
         if (pr == 1) return GFK_OK;
     }
@@ -949,11 +913,11 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
                            : use_chunked ? grid_for(kThreads, chunked_smem > 72 * 1024 ? 2 : 3)
                                          : grid_for(tiled_threads, tiled_smem > 50 * 1024 ? 2 : 4);
 
-    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws);
+    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail);
     a.step = 0;                                  // produces exchange 0
     thin_init_kernel<T, STRICT><<<grid_init, kThreads, 0, st>>>(a);
     GFK_CHECK_LAUNCH();
-    const bool nccl_exchange = a.n_ranks > 1 && !a.mail.enabled;
+    const bool nccl_exchange = a.n_ranks > 1 && !a.mail_enabled;
     for (int step = 1; step <= m; ++step) {
         // exchange the candidates of step-1 (peer mailboxes: inside the kernels), then continue or finish
         if (nccl_exchange) {

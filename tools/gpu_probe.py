@@ -51,7 +51,7 @@ def timed(fn, reps=3):
 
 warnings.simplefilter('ignore')
 timings = {}
-variants = [('persist', {}), ('persist-prefetch', {'GFK_PREFETCH': '1'}), ('multilaunch', {'GFK_PERSISTENT': '0'})]
+variants = [('persist', {}), ('multilaunch', {'GFK_PERSISTENT': '0'})]
 for cname, var in [(c, v) for c in ('c1', 'c2', 'c3', 'c5') for v in variants]:
     if cname == 'c5' and var[0] != 'multilaunch':
         continue
