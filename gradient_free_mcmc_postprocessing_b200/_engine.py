@@ -238,6 +238,7 @@ class SteinProblem:
             if timing is not None:
                 timing['loop_ms'] = e0.elapsed_time(e1)
                 timing['rows'] = r1 - r0
+                timing['ws'] = ws
         if return_objective:
             return out, objective
         return out

@@ -63,6 +63,7 @@ PROTOTYPES = {
     'gfk_p2p_local_handle': (ctypes.c_int, [_vp]),
     'gfk_p2p_open': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     'gfk_p2p_enabled': (ctypes.c_int, []),
+    'gfk_p2p_selftest': (ctypes.c_int, [ctypes.c_int, _pd, _vp]),
     'gfk_comm_size': (ctypes.c_int, []),
     'gfk_comm_rank': (ctypes.c_int, []),
     'gfk_allreduce_sum': (ctypes.c_int, [_vp, _i64, _vp]),

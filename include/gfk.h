@@ -154,6 +154,8 @@ int gfk_comm_init(int n_ranks, int rank, const void* id128_host, const char* ncc
 int gfk_p2p_local_handle(void* handle64_host);
 int gfk_p2p_open(const void* handles_host, int n_ranks, int rank);
 int gfk_p2p_enabled(void);
+/* collective: `iters` back-to-back mailbox exchanges with no other work; time per exchange in us (host out) */
+int gfk_p2p_selftest(int iters, double* us_per_exchange_host, void* stream);
 int gfk_comm_size(void);
 int gfk_comm_rank(void);
 int gfk_allreduce_sum(double* buf, int64_t count, void* stream);
