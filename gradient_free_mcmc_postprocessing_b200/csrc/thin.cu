@@ -138,6 +138,28 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long
     return v;
 }
 
+// Intra-GPU record: (value 64 bits, index 32 bits) in TWO self-validating words, each a 16-bit tag over a
+// 48-bit payload, moved with one 16-byte vector access (each 8-byte half is single-copy atomic and carries
+// its own tag, so a torn pair is simply seen as "not there yet").  One request per slot instead of three.
+__device__ __forceinline__ void slot_store(unsigned long long* p, unsigned tag16, double v, unsigned i) {
+    const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long t = (unsigned long long)(tag16 & 0xffffu) << 48;
+    const unsigned long long a = t | (vb >> 16);
+    const unsigned long long b = t | ((vb & 0xffffull) << 32) | (unsigned long long)i;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void slot_load(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ bool slot_ready(unsigned long long a, unsigned long long b, unsigned tag16) {
+    return (unsigned)(a >> 48) == (tag16 & 0xffffu) && (unsigned)(b >> 48) == (tag16 & 0xffffu);
+}
+__device__ __forceinline__ void slot_decode(unsigned long long a, unsigned long long b, double& v, unsigned& i) {
+    const unsigned long long vb = (a << 16) | ((b >> 32) & 0xffffull);
+    v = __longlong_as_double((long long)vb);
+    i = (unsigned)(b & 0xffffffffull);
+}
+
 __device__ __forceinline__ int mail_offset(const MailArgs& m, int exchange, int rank) {
     return (((m.job_parity * 2 + (exchange & 1)) * kMailRanks) + rank) * 4;
 }
@@ -656,15 +678,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         GFK_STAMP(step, 2);
         GFK_STAMP_CTA(step);
         {
-            const unsigned long long tag = (unsigned long long)(unsigned)(step + 1) << 32;
             unsigned long long (*slots_ll)[4] = ws->ll[step & 1];
-            if (tid == 0) {
-                const unsigned long long vb = (unsigned long long)__double_as_longlong(bv);
-                unsigned long long* w = slots_ll[blockIdx.x];
-                st_relaxed_gpu(w + 0, tag | (vb & 0xffffffffull));
-                st_relaxed_gpu(w + 1, tag | (vb >> 32));
-                st_relaxed_gpu(w + 2, tag | (unsigned long long)bi);
-            }
+            const unsigned tag16 = (unsigned)(step + 1);
+            if (tid == 0) slot_store(slots_ll[blockIdx.x], tag16, bv, bi);
             if (tid < 32) {
                 double wv = __longlong_as_double(0x7ff0000000000000LL);
                 unsigned wi = 0xffffffffu;
@@ -676,7 +692,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                     // and re-publishes the global winner for the other CTAs (measured: fewer pollers on lines a
                     // peer writes, 16.0 -> 12.4 us per step at 2 x 0.5 M rows).  Lane l owns slots l, l+32, ... and
                     // requests all their words together, so a polling round costs one L2 latency.
-                    unsigned long long w0[kPollPerLane], w1[kPollPerLane], w2[kPollPerLane];
+                    unsigned long long w0[kPollPerLane], w1[kPollPerLane];
                     unsigned pending = 0;
 #pragma unroll
                     for (int q = 0; q < kPollPerLane; ++q)
@@ -687,18 +703,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
 #pragma unroll
                         for (int q = 0; q < kPollPerLane; ++q) {
                             if (pending & (1u << q)) {
-                                const unsigned long long* w = slots_ll[tid + 32 * q];
-                                w0[q] = ld_relaxed_gpu(w + 0); w1[q] = ld_relaxed_gpu(w + 1); w2[q] = ld_relaxed_gpu(w + 2);
+                                slot_load(slots_ll[tid + 32 * q], w0[q], w1[q]);
                             }
                         }
 #pragma unroll
                         for (int q = 0; q < kPollPerLane; ++q) {
-                            if ((pending & (1u << q)) && (w0[q] >> 32) == (tag >> 32) && (w1[q] >> 32) == (tag >> 32) &&
-                                (w2[q] >> 32) == (tag >> 32)) {
+                            if ((pending & (1u << q)) && slot_ready(w0[q], w1[q], tag16)) {
                                 pending &= ~(1u << q);
-                                const double pv = __longlong_as_double(
-                                    (long long)(((w1[q] & 0xffffffffull) << 32) | (w0[q] & 0xffffffffull)));
-                                const unsigned pi = (unsigned)(w2[q] & 0xffffffffull);
+                                double pv;
+                                unsigned pi;
+                                slot_decode(w0[q], w1[q], pv, pi);
                                 if (cand_better(pv, pi, wv, wi)) { wv = pv; wi = pi; }
                             }
                         }
@@ -715,29 +729,22 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                         wi = g.i;
                     }
                     // broadcast: one flag-in-data slot that the other CTAs poll
-                    if (MULTI && tid == 0) {
-                        const unsigned long long vb = (unsigned long long)__double_as_longlong(wv);
-                        st_relaxed_gpu(bc + 0, tag | (vb & 0xffffffffull));
-                        st_relaxed_gpu(bc + 1, tag | (vb >> 32));
-                        st_relaxed_gpu(bc + 2, tag | (unsigned long long)wi);
-                    }
+                    if (MULTI && tid == 0) slot_store(bc, tag16, wv, wi);
                 } else {
-                    unsigned long long w0 = 0, w1 = 0, w2 = 0;
+                    unsigned long long w0 = 0, w1 = 0;
                     if (tid == 0) {
                         unsigned spins = 0;
 #pragma unroll 1
                         for (;;) {
-                            w0 = ld_relaxed_gpu(bc + 0); w1 = ld_relaxed_gpu(bc + 1); w2 = ld_relaxed_gpu(bc + 2);
-                            if ((w0 >> 32) == (tag >> 32) && (w1 >> 32) == (tag >> 32) && (w2 >> 32) == (tag >> 32)) break;
+                            slot_load(bc, w0, w1);
+                            if (slot_ready(w0, w1, tag16)) break;
                             if (++spins > kSpinLimit || ld_volatile_u32(&ws->abort)) { dead = true; break; }
                         }
                     }
                     dead = __any_sync(0xffffffffu, dead);
                     w0 = __shfl_sync(0xffffffffu, w0, 0);
                     w1 = __shfl_sync(0xffffffffu, w1, 0);
-                    w2 = __shfl_sync(0xffffffffu, w2, 0);
-                    wv = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
-                    wi = (unsigned)(w2 & 0xffffffffull);
+                    slot_decode(w0, w1, wv, wi);
                 }
                 GFK_STAMP(step, 4);
                 if (tid == 0) {
