@@ -62,13 +62,16 @@ __global__ void __launch_bounds__(kRedThreads) col_chunk_sum_kernel(const double
     if (bad) atomicAdd(nonfinite, (unsigned long long)bad);
 }
 
-// out[k] = (sum of the chunk partials in index order) / n
+// out[k] = (sum of the chunk partials, fixed order) / n
+// (one warp per column: lane l adds partials l, l+32, ... in index order, then a fixed shuffle tree)
 __global__ void col_finish_kernel(const double* __restrict__ partial, int nchunks, int d, long long n,
                                   double* __restrict__ out) {
-    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int k = warp; k < d; k += nwarps) {
         double acc = 0.0;
-        for (int c = 0; c < nchunks; ++c) acc += partial[(long long)c * d + k];
-        out[k] = acc / (double)n;
+        for (int c = lane; c < nchunks; c += 32) acc += partial[(long long)c * d + k];
+        acc = warp_sum(acc);
+        if (lane == 0) out[k] = acc / (double)n;
     }
 }
 
@@ -118,41 +121,79 @@ __global__ void __launch_bounds__(256) pdist_kernel(const double* __restrict__ x
     }
 }
 
-// radix select on the bit patterns of non-negative doubles: block b finds order statistic rank[b]
-__global__ void __launch_bounds__(1024) radix_select_kernel(const double* __restrict__ dist, long long count,
-                                                            long long rank0, long long rank1,
-                                                            double* __restrict__ out) {
-    __shared__ unsigned hist[256];
-    __shared__ unsigned long long prefix_sh;
-    __shared__ long long rank_sh;
+// ---- exact order statistics by radix select on the bit patterns of non-negative doubles ---------------
+// Six passes of 11 bits (the last 9): every pass histograms the keys that match the prefix found so far
+// (per-block shared-memory histograms merged with global atomics, all SMs busy), then one block scans the
+// 2048 bins to extend the prefix.  Two ranks (the two middle order statistics) are tracked together.
+constexpr int kSelBits = 11;
+constexpr int kSelBins = 1 << kSelBits;
+struct SelState {
+    unsigned long long prefix[2];
+    long long rank[2];
+};
+
+__global__ void __launch_bounds__(256) select_hist_kernel(const double* __restrict__ dist, long long count, int shift,
+                                                          int width, const SelState* __restrict__ state,
+                                                          unsigned* __restrict__ hist /* [2][kSelBins] */) {
+    __shared__ unsigned sh[2][kSelBins];
+    for (int b = threadIdx.x; b < 2 * kSelBins; b += blockDim.x) (&sh[0][0])[b] = 0;
+    __syncthreads();
     const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(dist);
+    const unsigned long long himask = (shift + width >= 64) ? 0ull : (~0ull << (shift + width));
+    const unsigned long long p0 = state->prefix[0], p1 = state->prefix[1];
+    const unsigned mask = (1u << width) - 1u;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count;
+         e += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[e];
+        const unsigned bin = (unsigned)(key >> shift) & mask;
+        if ((key & himask) == p0) atomicAdd(&sh[0][bin], 1u);
+        if ((key & himask) == p1) atomicAdd(&sh[1][bin], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 2 * kSelBins; b += blockDim.x) {
+        const unsigned v = (&sh[0][0])[b];
+        if (v) atomicAdd(&hist[b], v);
+    }
+}
+
+// one block: for each rank, the bin whose cumulative count first exceeds the rank; clears hist for the next pass
+__global__ void __launch_bounds__(1024) select_pick_kernel(unsigned* __restrict__ hist, int shift, SelState* state,
+                                                           double* __restrict__ out, int last) {
+    __shared__ unsigned long long partial[1024];
+    for (int r = 0; r < 2; ++r) {
+        unsigned* h = hist + r * kSelBins;
+        // thread t owns bins 2t, 2t+1
+        const unsigned c0 = h[2 * threadIdx.x], c1 = h[2 * threadIdx.x + 1];
+        partial[threadIdx.x] = (unsigned long long)c0 + c1;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {          // inclusive scan
+            const unsigned long long add = (threadIdx.x >= off) ? partial[threadIdx.x - off] : 0ull;
+            __syncthreads();
+            partial[threadIdx.x] += add;
+            __syncthreads();
+        }
+        const long long before = (long long)(partial[threadIdx.x] - c0 - c1);   // keys in bins < 2t
+        const long long rank = state->rank[r];
+        __syncthreads();
+        if (rank >= before && rank < before + (long long)c0 + c1) {
+            const int bin = (rank < before + (long long)c0) ? 2 * threadIdx.x : 2 * threadIdx.x + 1;
+            state->rank[r] = rank - before - (bin & 1 ? (long long)c0 : 0);
+            state->prefix[r] |= (unsigned long long)bin << shift;
+            if (last) out[r] = __longlong_as_double((long long)state->prefix[r]);
+        }
+        h[2 * threadIdx.x] = 0;
+        h[2 * threadIdx.x + 1] = 0;
+        __syncthreads();
+    }
+}
+
+__global__ void select_init_kernel(SelState* state, unsigned* hist, long long rank0, long long rank1) {
+    for (int b = threadIdx.x; b < 2 * kSelBins; b += blockDim.x) hist[b] = 0;
     if (threadIdx.x == 0) {
-        prefix_sh = 0ull;
-        rank_sh = blockIdx.x == 0 ? rank0 : rank1;
+        state->prefix[0] = state->prefix[1] = 0ull;
+        state->rank[0] = rank0;
+        state->rank[1] = rank1;
     }
-    for (int shift = 56; shift >= 0; shift -= 8) {
-        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-        __syncthreads();
-        const unsigned long long prefix = prefix_sh;
-        const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
-        for (long long e = threadIdx.x; e < count; e += blockDim.x) {
-            const unsigned long long key = keys[e];
-            if ((key & himask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & 0xffu)], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long r = rank_sh;
-            int b = 0;
-            for (; b < 256; ++b) {
-                if (r < (long long)hist[b]) break;
-                r -= hist[b];
-            }
-            rank_sh = r;
-            prefix_sh = prefix | ((unsigned long long)b << shift);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[blockIdx.x] = __longlong_as_double((long long)prefix_sh);
 }
 
 __global__ void to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, long long count) {
@@ -268,7 +309,8 @@ extern "C" int gfk_standardize(const double* x, const double* g, int64_t n, int3
 
 extern "C" size_t gfk_median_ws_bytes(int64_t n, int32_t cap) {
     const int64_t R = n > cap ? cap : n;
-    return 64 + sizeof(long long) * (size_t)R + sizeof(double) * (size_t)(R * (R - 1) / 2 + 2);
+    return 64 + sizeof(SelState) + sizeof(unsigned) * 2 * kSelBins + sizeof(long long) * (size_t)R +
+           sizeof(double) * (size_t)(R * (R - 1) / 2 + 2);
 }
 
 extern "C" int gfk_median_pdist(const double* x, int64_t n, int32_t d, int32_t cap, double* mid_host, void* ws,
@@ -287,7 +329,9 @@ extern "C" int gfk_median_pdist(const double* x, int64_t n, int32_t d, int32_t c
         for (int a = 0; a < R; ++a) rows[a] = a;
     }
     double* out2 = reinterpret_cast<double*>(ws);  // two order statistics
-    long long* rows_dev = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 64);
+    SelState* state = reinterpret_cast<SelState*>(reinterpret_cast<char*>(ws) + 64);
+    unsigned* hist = reinterpret_cast<unsigned*>(state + 1);
+    long long* rows_dev = reinterpret_cast<long long*>(hist + 2 * kSelBins);
     double* dist = reinterpret_cast<double*>(rows_dev + R);
     // keep dist 8-byte aligned (rows_dev is 8-byte elements at a 64-byte offset)
     GFK_CUDA(cudaMemcpyAsync(rows_dev, rows.data(), sizeof(long long) * R, cudaMemcpyHostToDevice, st));
@@ -296,8 +340,16 @@ extern "C" int gfk_median_pdist(const double* x, int64_t n, int32_t d, int32_t c
     // np.median: mean of the two middle order statistics (equal ranks when the count is odd)
     const long long k1 = npairs / 2;
     const long long k0 = (npairs % 2 == 0) ? k1 - 1 : k1;
-    radix_select_kernel<<<2, 1024, 0, st>>>(dist, npairs, k0, k1, out2);
-    count_launches(2);
+    select_init_kernel<<<1, 1024, 0, st>>>(state, hist, k0, k1);
+    int launches = 2;
+    for (int hi = 64; hi > 0; hi -= kSelBits) {
+        const int shift = hi - kSelBits > 0 ? hi - kSelBits : 0;
+        const int width = hi - shift;
+        select_hist_kernel<<<grid_for(npairs, 256), 256, 0, st>>>(dist, npairs, shift, width, state, hist);
+        select_pick_kernel<<<1, 1024, 0, st>>>(hist, shift, state, out2, shift == 0);
+        launches += 2;
+    }
+    count_launches(launches);
     GFK_CHECK_LAUNCH();
     GFK_CUDA(cudaMemcpyAsync(mid_host, out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     GFK_CUDA(cudaStreamSynchronize(st));  // also keeps `rows` alive until the copy has been consumed

@@ -77,8 +77,8 @@ int gfk_device_info(int* cc, int* sm_count, char* name, int name_len);
 /* ---- a3: stein_thinning.thinning._validate_and_standardize ------------------------
  * loc = mean(x), scl = mean(|x - loc|) per column; x_out = x / scl, g_out = g * scl.
  * With standardize = 0 the data are copied unchanged (scl = 1).  Also counts
- * non-finite entries of x and g.  Reduction order: fixed 2048-row chunks, then the
- * chunk partials in index order - deterministic and independent of the GPU count, but
+ * non-finite entries of x and g.  Reduction order: fixed 2048-row chunks, then a fixed
+ * tree over the chunk partials - deterministic and independent of the GPU count, but
  * not numpy's strictly sequential order ("standardisation").
  * SYNCHRONOUS: scl_host (d doubles, host) is valid on return.  Returns GFK_ENUMERIC if
  * any input is non-finite or (standardize and min(scl) == 0).
