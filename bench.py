@@ -308,7 +308,8 @@ def run_ours(args):
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(f'thin_step:{args.precision}:bytes_per_launch')
-        h2d = sum(int(np.prod(s)) * 8 for s in ((n_total, D), (n_total, D), (n_total,), (n_total,)))
+        # host inputs: each rank uploads its 1/N block of rows over PCIe and all-gathers the rest over NVLink
+        h2d = sum(int(np.prod(s)) * 8 for s in ((n_total, D), (n_total, D), (n_total,), (n_total,))) // world
         line = {
             'metric': 'stein_kernel_pair_evals_per_s', 'value': value, 'unit': 'pair-evals/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -320,7 +321,8 @@ def run_ours(args):
                        'thinning_wall_time_ms': ms_per_step, 'l2': 'flushed between timed steps (512 MiB write)',
                        'step': 'one full thinning job n->m (standardise + median + log-weights + m greedy steps)'},
             'e2e': {'value': pairs / (e2e_ms_per_step * 1e-3), 'unit': 'pair-evals/s', 'ms_per_step': e2e_ms_per_step,
-                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * M},
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * M,
+                    'bytes_are': 'per rank'},
             'gpu_launches': int(res['launches']),
             'clocks': res['clocks'],
             'roofline': {'bound': 'hbm', 'kernel': 'thin_persistent_kernel', 'achieved': achieved, 'peak': peak_gbs,

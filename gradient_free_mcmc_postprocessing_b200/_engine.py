@@ -50,6 +50,27 @@ def _to_device_f64(a, device, name):
     return torch.from_numpy(arr).to(device, non_blocking=False)
 
 
+def _replicate_from_host(a, device, lib):
+    """Multi-GPU: every rank needs the full replica, but only 1/R of it has to cross PCIe on each rank -
+    upload this rank's block of rows and all-gather the rest over NVLink (torch.distributed plumbing)."""
+    import torch.distributed as dist
+    world, rank = lib.gfk_comm_size(), lib.gfk_comm_rank()
+    host = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.float64))
+    if host.dtype != torch.float64:
+        host = host.to(torch.float64)
+    host = host.contiguous()
+    n = host.shape[0]
+    per = -(-n // world)
+    begin, end = min(rank * per, n), min((rank + 1) * per, n)
+    tail = tuple(host.shape[1:])
+    mine = torch.zeros((per,) + tail, dtype=torch.float64, device=device)
+    if end > begin:
+        mine[:end - begin].copy_(host[begin:end], non_blocking=True)
+    full = torch.empty((per * world,) + tail, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(full, mine)
+    return full[:n] if per * world != n else full
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -107,8 +128,9 @@ class SteinProblem:
         self.n, self.d = n, d
 
         with torch.cuda.device(device):
-            x_raw = _to_device_f64(sample, device, 'sample')
-            g_raw = _to_device_f64(gradient, device, 'gradient')
+            load = self._loader(sample, device, lib)
+            x_raw = load(sample, device, 'sample')
+            g_raw = load(gradient, device, 'gradient')
             st = _stream_ptr(device)
             # a3: validation + standardisation
             self.x = torch.empty_like(x_raw)
@@ -127,8 +149,8 @@ class SteinProblem:
             # a4: gradient-free log-weights
             self.lw = self.w = None
             if self.gf:
-                lp = _to_device_f64(log_p, device, 'log_p')
-                lq = _to_device_f64(log_q, device, 'log_q')
+                lp = load(log_p, device, 'log_p')
+                lq = load(log_q, device, 'log_q')
                 self.lw = torch.empty(n, dtype=torch.float64, device=device)
                 spread = ctypes.c_double(0.0)
                 lws = _bytes(lib.gfk_log_weights_ws_bytes(), device)
@@ -142,6 +164,21 @@ class SteinProblem:
                     warnings.warn(f'log_q differs from log_p by more than {WEIGHT_SCALE_THRESHOLD} - '
                                   'consider using q that matches target better')
             self._finalise_dtype()
+
+    @staticmethod
+    def _loader(sample, device, lib):
+        """Host inputs on a multi-rank communicator are uploaded in shards and all-gathered over NVLink."""
+        on_host = not (isinstance(sample, torch.Tensor) and sample.is_cuda)
+        if on_host and lib.gfk_comm_size() > 1:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_backend() == 'nccl' \
+                    and dist.get_world_size() == lib.gfk_comm_size():
+                def sharded(a, dev, name):
+                    if isinstance(a, torch.Tensor) and a.is_cuda:
+                        return _to_device_f64(a, dev, name)
+                    return _replicate_from_host(a, dev, lib).contiguous()
+                return sharded
+        return _to_device_f64
 
     # -- preconditioner -------------------------------------------------------------------------
     def _set_preconditioner(self, preconditioner):

@@ -32,9 +32,9 @@ struct __align__(16) ThinWs {
     unsigned pad_;
     // persistent kernel, flag-in-data slots: every 8-byte word carries (tag << 32 | payload), so a reader
     // that sees the expected tag in all three words has the whole record - no fences, no atomics
-    unsigned long long ll[2][kMaxBlocks / 2][4];
+    __align__(16) unsigned long long ll[2][kMaxBlocks / 2][4];
     MailArgs mail;           // peer mailboxes of this job (written by thin_reset_kernel)
-    unsigned long long bcast[2][4];   // persistent multi-rank kernel: CTA 0 re-publishes the global winner here
+    __align__(16) unsigned long long bcast[2][4];   // persistent multi-rank kernel: CTA 0 re-publishes the global winner here
 #ifdef GFK_TRACE
     long long trace[128][8];          // development builds: globaltimer (ns) of CTA 0 / thread 0 per step and phase
     long long trace_cta[64][160];     // globaltimer at which each CTA published its block minimum, steps 32..95
