@@ -271,6 +271,7 @@ class SteinProblem:
                                _stream_ptr(self.device)))
             if timing is not None:
                 e1.record()
+            check(lib.gfk_thin_check(_ptr(ws), _stream_ptr(self.device)))
             out = idx.cpu().numpy().view(np.uint32)
             if timing is not None:
                 timing['loop_ms'] = e0.elapsed_time(e1)

@@ -54,6 +54,7 @@ PROTOTYPES = {
     'gfk_exp_weights': (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _vp]),
     'gfk_thin_ws_bytes': (_sz, []),
     'gfk_thin': (ctypes.c_int, [_pp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
+    'gfk_thin_check': (ctypes.c_int, [_vp, _vp]),
     'gfk_ksd_rowsums': (ctypes.c_int, [_pp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'gfk_ksd_finish': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'gfk_kmat': (ctypes.c_int, [_pp, _vp, _i64, _vp, _vp]),

@@ -6,7 +6,8 @@
 //
 // gfk_ksd_rowsums: one CTA per 64-row tile I walks the column tiles J <= I.  Row and column tiles
 // are staged in shared memory transposed ([k][row], conflict-free), in chunks of KC dimensions so any
-// d fits; each thread owns a 4 x 4 block of pairs and keeps the three running dot products
+// d fits; each thread owns 4 rows x 4 columns (columns strided by 16, so a half-warp reads one conflict-free
+// 128-byte line per shared-memory load) and keeps the three running dot products
 // (<r,r>, <ds,r>, <sx,sy>) of every pair in registers - a GEMM-shaped loop on the FP64 (or FP32)
 // FMA pipe with ~0 bytes of HBM traffic per pair.  Row sums are reduced in a fixed order (no
 // atomics), so results are run-to-run reproducible and independent of the GPU count.
@@ -174,11 +175,11 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
             for (int i = 0; i < MT; ++i) {
                 xi[i] = xr[k * LD + ty * MT + i];
                 si[i] = sr[k * LD + ty * MT + i];
-                xj[i] = xc[k * LD + tx * MT + i];
-                sj[i] = sc[k * LD + tx * MT + i];
+                xj[i] = xc[k * LD + tx + (TILE / MT) * i];
+                sj[i] = sc[k * LD + tx + (TILE / MT) * i];
                 if (DENSE) {
                     li[i] = xlr[k * LD + ty * MT + i];
-                    lj[i] = xlc[k * LD + tx * MT + i];
+                    lj[i] = xlc[k * LD + tx + (TILE / MT) * i];
                 }
             }
 #pragma unroll
@@ -208,10 +209,10 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
                 double part_sum = 0.0;
 #pragma unroll
                 for (int j = 0; j < MT; ++j) {
-                    const long long b = c0 + tx * MT + j;
+                    const long long b = c0 + tx + (TILE / MT) * j;
                     T kv = fast_finish<T, DENSE>(rr[i][j], DENSE ? uu[i][j] : T(0), su[i][j], ss[i][j], a.kp);
                     if (gf) {
-                        const T wi = wr[ty * MT + i], wj = wc[tx * MT + j];
+                        const T wi = wr[ty * MT + i], wj = wc[tx + (TILE / MT) * j];
                         kv *= pre_w ? (wi * wj) : (T)exp((double)wi + (double)wj);
                     }
                     if (b < t && t < a.m) part_sum += (double)kv;

@@ -11,6 +11,7 @@
 // (algorithmic traffic 16d + 16 (+8) bytes per row in float64), adds 2 k(x_i, y) to A_i and
 // keeps a running (min, first index).  Warp shuffle -> block -> last-block-done grid reduction
 // produces the rank's candidate for the next exchange.  No host round trip inside the loop.
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -40,6 +41,10 @@ struct __align__(16) ThinWs {
     long long trace_cta[64][160];     // globaltimer at which each CTA published its block minimum, steps 32..95
 #endif
 };
+
+static_assert(offsetof(ThinWs, ll) % 16 == 0 && offsetof(ThinWs, bcast) % 16 == 0 && sizeof(ThinWs::ll[0][0]) == 32,
+              "flag-in-data slots are moved with 16-byte vector accesses");
+static_assert(offsetof(ThinWs, send) % 16 == 0 && offsetof(ThinWs, recv) % 16 == 0, "Cand records are 16-byte aligned");
 
 #ifdef GFK_TRACE
 __device__ __forceinline__ long long gfk_now() {
@@ -1068,6 +1073,22 @@ extern "C" int gfk_p2p_selftest(int iters, double* us_per_exchange_host, void* s
 
 extern "C" size_t gfk_thin_ws_bytes(void) { return sizeof(gfk::ThinWs); }
 
+extern "C" int gfk_thin_check(const void* ws, void* stream) {
+    using namespace gfk;
+    GFK_REQUIRE(ws, "gfk_thin_check: NULL workspace");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned flag = 0;
+    GFK_CUDA(cudaMemcpyAsync(&flag, static_cast<const char*>(ws) + offsetof(ThinWs, abort), sizeof(flag),
+                             cudaMemcpyDeviceToHost, st));
+    GFK_CUDA(cudaStreamSynchronize(st));
+    if (flag) {
+        set_error("gfk_thin: the persistent kernel gave up waiting for a block or a peer rank (exchange timed out); "
+                  "the index vector is invalid");
+        return GFK_ECUDA;
+    }
+    return GFK_OK;
+}
+
 extern "C" int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end, int32_t m,
                         double* objective, uint32_t* idx_out, void* ws, void* stream) {
     using namespace gfk;
@@ -1080,6 +1101,18 @@ extern "C" int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end
                 (long long)p->n);
     GFK_REQUIRE(!(p->xl && p->mode == GFK_F64_STRICT),
                 "gfk_thin: a dense preconditioner needs a fast mode (numpy's BLAS order is not reproducible)");
+    GFK_REQUIRE(reinterpret_cast<uintptr_t>(ws) % 16 == 0, "gfk_thin: ws must be 16-byte aligned");
+    {
+        const size_t esz = p->mode == GFK_F32_FAST ? sizeof(float) : sizeof(double);
+        const size_t row_bytes = (size_t)p->d * esz;
+        // small-d kernels read rows with 16-byte vector loads whenever the row size allows it
+        if (p->d <= 4 && row_bytes % 16 == 0)
+            GFK_REQUIRE(reinterpret_cast<uintptr_t>(p->x) % 16 == 0 && reinterpret_cast<uintptr_t>(p->s) % 16 == 0,
+                        "gfk_thin: x and s must be 16-byte aligned for d = %d", p->d);
+        else if (p->d <= 4 && row_bytes % 8 == 0)
+            GFK_REQUIRE(reinterpret_cast<uintptr_t>(p->x) % 8 == 0 && reinterpret_cast<uintptr_t>(p->s) % 8 == 0,
+                        "gfk_thin: x and s must be 8-byte aligned for d = %d", p->d);
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (p->mode) {
         case GFK_F64_STRICT: return thin_typed<double, true>(p, row_begin, row_end, m, objective, idx_out, ws, st);

@@ -122,6 +122,9 @@ int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f32, void* st
  *   ws        : device scratch of gfk_thin_ws_bytes() bytes
  * Asynchronous on `stream`. */
 size_t gfk_thin_ws_bytes(void);
+/* SYNCHRONOUS: after gfk_thin on the same stream and workspace - non-zero if the single-launch kernel abandoned an
+ * exchange (a block or a peer rank never arrived within the spin limit); idx_out is then invalid */
+int gfk_thin_check(const void* ws, void* stream);
 int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end, int32_t m,
              double* objective, uint32_t* idx_out, void* ws, void* stream);
 

@@ -80,3 +80,40 @@ def _worker(rank, world, port, n, seed):
 @pytest.mark.timeout(120)
 def test_sharded_exchange_world2_gloo():
     mp.spawn(_worker, args=(2, _free_port(), 1001, 7), nprocs=2, join=True)
+
+
+class _FakeComm:
+    def __init__(self, world, rank):
+        self.world, self.rank = world, rank
+
+    def gfk_comm_size(self):
+        return self.world
+
+    def gfk_comm_rank(self):
+        return self.rank
+
+
+def _replicate_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from gradient_free_mcmc_postprocessing_b200._engine import _replicate_from_host
+        rng = np.random.default_rng(5)
+        for n in (7, 8, 1001):                     # ragged and even splits
+            for shape in ((n, 4), (n,)):
+                a = rng.standard_normal(shape)
+                full = _replicate_from_host(a, torch.device('cpu'), _FakeComm(world, rank))
+                assert tuple(full.shape) == shape and full.dtype == torch.float64
+                assert np.array_equal(full.numpy(), a), (rank, n, shape)
+                t = torch.from_numpy(a.astype(np.float32))          # dtype conversion path
+                full = _replicate_from_host(t, torch.device('cpu'), _FakeComm(world, rank))
+                assert np.array_equal(full.numpy(), a.astype(np.float32).astype(np.float64))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_host_upload_reassembles_replica_world2_and_3():
+    """The shard-upload + all-gather used for host inputs on multi-GPU runs (here on CPU tensors over gloo)."""
+    mp.spawn(_replicate_worker, args=(2, _free_port()), nprocs=2, join=True)
+    mp.spawn(_replicate_worker, args=(3, _free_port()), nprocs=3, join=True)
