@@ -248,6 +248,32 @@ __global__ void lw_apply_kernel(const double* __restrict__ log_p, const double* 
     }
 }
 
+// ---- Gaussian proxy of gaussian_thin (reference: code/src/thinning.py:15-16) -----------------
+// log_q[i] = -0.5 (cst + (x_i - mean)' P (x_i - mean)),  grad_q[i] = -P (x_i - mean),  P = cov^-1.
+// Thread per row; mean and P are staged in shared memory; sums run over j in index order without contraction.
+__global__ void __launch_bounds__(256) gaussian_proxy_kernel(const double* __restrict__ x, long long n, int d,
+                                                             const double* __restrict__ mean,
+                                                             const double* __restrict__ prec, double cst,
+                                                             double* __restrict__ log_q, double* __restrict__ grad_q) {
+    extern __shared__ double gp_sm[];
+    double* mean_s = gp_sm;
+    double* prec_s = gp_sm + d;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) mean_s[e] = mean[e];
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) prec_s[e] = prec[e];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double* xi = x + i * d;
+        double maha = 0.0;
+        for (int k = 0; k < d; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < d; ++j) acc = __dadd_rn(acc, __dmul_rn(prec_s[k * d + j], __dsub_rn(xi[j], mean_s[j])));
+            grad_q[i * d + k] = -acc;
+            maha = __dadd_rn(maha, __dmul_rn(__dsub_rn(xi[k], mean_s[k]), acc));
+        }
+        log_q[i] = __dmul_rn(-0.5, __dadd_rn(cst, maha));
+    }
+}
+
 static int grid_for(long long work, int threads) {
     long long b = (work + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 8;
@@ -407,6 +433,20 @@ extern "C" int gfk_log_weights(const double* log_p, const double* log_q, int64_t
     *spread_host = mx - mn;
     lw_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(log_p, log_q, n, use_cap, mx, range_cap, lw);
     count_launches(2);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" int gfk_gaussian_proxy(const double* x, int64_t n, int32_t d, const double* mean, const double* prec,
+                                  double cst, double* log_q, double* grad_q, void* stream) {
+    GFK_REQUIRE(x && mean && prec && log_q && grad_q, "gfk_gaussian_proxy: NULL pointer argument");
+    GFK_REQUIRE(n >= 1 && d >= 1 && d <= 160, "gfk_gaussian_proxy: need n >= 1 and 1 <= d <= 160");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = sizeof(double) * (size_t)(d + d * d);
+    if (smem > 48 * 1024)
+        GFK_CUDA(cudaFuncSetAttribute(gaussian_proxy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gaussian_proxy_kernel<<<grid_for(n, 256), 256, smem, st>>>(x, n, d, mean, prec, cst, log_q, grad_q);
+    count_launches(1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }

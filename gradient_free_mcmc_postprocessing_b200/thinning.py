@@ -57,12 +57,48 @@ def thin_gf(sample, log_p, log_q, gradient_q, n_points, standardize=True, precon
     return _greedy_search(n_points, integrand)
 
 
-def gaussian_thin(sample, log_p, mean, cov, thinned_size, range_cap=200, *, precision=None, device=None):
+def gaussian_proxy_device(sample, mean, cov, *, device=None):
+    """The Gaussian proxy's log-density and score on the device: returns CUDA
+    tensors ``(sample_dev, log_q, gradient_q)``.  The d x d inverse and log-determinant stay on the host."""
+    import ctypes
+    from . import _lib
+    from ._engine import _ptr, _require_cuda, _stream_ptr, _to_device_f64
+    lib = _lib.load()
+    dev = _require_cuda(device)
+    cov = np.atleast_2d(np.asarray(cov, dtype=float))
+    mean = np.atleast_1d(np.asarray(mean, dtype=float))
+    d = mean.shape[0]
+    if cov.shape != (d, d) or tuple(sample.shape)[1:] != (d,):
+        raise ValueError('inconsistent shapes of sample, mean and cov')
+    sign, logdet = np.linalg.slogdet(cov)
+    if sign <= 0:
+        raise np.linalg.LinAlgError('cov must be symmetric positive definite')
+    cst = d * np.log(2 * np.pi) + logdet
+    with torch.cuda.device(dev):
+        x = _to_device_f64(sample, dev, 'sample')
+        n = x.shape[0]
+        mean_dev = torch.from_numpy(mean).to(dev)
+        prec_dev = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(cov))).to(dev)
+        log_q = torch.empty(n, dtype=torch.float64, device=dev)
+        grad_q = torch.empty((n, d), dtype=torch.float64, device=dev)
+        _lib.check(lib.gfk_gaussian_proxy(_ptr(x), n, d, _ptr(mean_dev), _ptr(prec_dev), ctypes.c_double(cst),
+                                          _ptr(log_q), _ptr(grad_q), _stream_ptr(dev)))
+    return x, log_q, grad_q
+
+
+def gaussian_thin(sample, log_p, mean, cov, thinned_size, range_cap=200, *, precision=None, device=None,
+                  proxy_on_device=False):
     """Gaussian-proxy gradient-free thinning (reference: code/src/thinning.py:14-17).
 
-    The proxy's log-density and score are O(n d^2) host-side numpy here exactly as in the reference
-    (scipy ``mvn.logpdf`` + einsum); moving them onto the device is SURVEY.md section 8f item 1.
+    By default the proxy's log-density and score are computed on the host exactly as in the reference (scipy
+    ``mvn.logpdf`` + einsum).  ``proxy_on_device=True`` computes them with ``gfk_gaussian_proxy`` instead, which
+    also removes the host-to-device copy of ``log_q`` / ``gradient_q`` (added in
+    round 1 without GPU access, so it is opt-in until it has been measured).
     """
+    if proxy_on_device:
+        x_dev, log_q, gradient_q = gaussian_proxy_device(sample, mean, cov, device=device)
+        return thin_gf(x_dev, log_p, log_q, gradient_q, thinned_size, range_cap=range_cap, preconditioner='med',
+                       precision=precision, device=device)
     from scipy.stats import multivariate_normal as mvn
     sample_np = sample.cpu().numpy() if isinstance(sample, torch.Tensor) else np.asarray(sample)
     log_q = mvn.logpdf(sample_np, mean=mean, cov=cov)

@@ -111,6 +111,13 @@ int gfk_log_weights(const double* log_p, const double* log_q, int64_t n, int use
                     double* lw, double* spread_host, void* ws, void* stream);
 int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f32, void* stream);
 
+/* ---- next: the Gaussian proxy of gaussian_thin, code/src/thinning.py:15-16 ----------------
+ * log_q[i] = -0.5 (cst + (x_i - mean)' P (x_i - mean)) with cst = d log(2 pi) + log det(cov) (what scipy's
+ * mvn.logpdf evaluates), grad_q[i] = -P (x_i - mean), P = cov^-1.  x (n, d) RAW sample, mean (d) and prec (d, d
+ * row-major) on the device.  Asynchronous.  [added in round 1 without GPU access: verified on the host only] */
+int gfk_gaussian_proxy(const double* x, int64_t n, int32_t d, const double* mean, const double* prec, double cst,
+                       double* log_q, double* grad_q, void* stream);
+
 /* ---- a5 + a4: stein_thinning.thinning._greedy_search over the fused integrand -------
  * Greedy selection of m indices (with replacement, first-index tie-break = np.argmin):
  *   A_i = k(i, i);  idx[0] = argmin A;  repeat  A_i += 2 k(i, idx[t-1]);  idx[t] = argmin A.
