@@ -18,10 +18,7 @@ namespace gfk {
 constexpr int kChunkRows = 2048;
 constexpr int kRedThreads = 256;
 
-struct StdWs {
-    unsigned long long nonfinite;
-    // followed by: loc[d], scl[d], partial[nchunks][d]
-};
+// standardisation workspace: [nonfinite counter | 64 B] loc[d] scl[d] partial[nchunks][d]
 
 __device__ __forceinline__ double block_sum_256(double v, double* sh) {
     v = warp_sum(v);

@@ -133,16 +133,6 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     return *reinterpret_cast<const volatile unsigned*>(p);
 }
 
-// GPU-scope relaxed accesses for the intra-GPU flag-in-data slots (L1 is bypassed; no system-scope traffic)
-__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // Intra-GPU record: (value 64 bits, index 32 bits) in TWO self-validating words, each a 16-bit tag over a
 // 48-bit payload, moved with one 16-byte vector access (each 8-byte half is single-copy atomic and carries
 // its own tag, so a torn pair is simply seen as "not there yet").  One request per slot instead of three.
