@@ -118,3 +118,61 @@ def test_install_as_stein_thinning_aliases():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+class _FakeProblem:
+    """Stands in for a device-resident SteinProblem: k(i, j) = table[i, j], so the integrand's index plumbing
+    (slices, lists, broadcasting, re-indexing) can be checked on the CPU."""
+
+    def __init__(self, n, seed=0):
+        rng = np.random.default_rng(seed)
+        a = rng.standard_normal((n, n))
+        self.table, self.n = a + a.T, n
+        self.calls = []
+
+    def pairs(self, ia, ib):
+        self.calls.append((np.shape(ia), np.shape(ib)))
+        return self.table[np.asarray(ia), np.asarray(ib)]
+
+    def ksd(self, sel, m):
+        sel = np.arange(m) if sel is None else np.asarray(sel)
+        sub = self.table[np.ix_(sel, sel)]
+        return np.array([np.sqrt(abs(sub[:t + 1, :t + 1].sum())) / (t + 1) for t in range(m)])
+
+    def kmat(self, sel, m):
+        sel = np.arange(m) if sel is None else np.asarray(sel)
+        return self.table[np.ix_(sel, sel)]
+
+
+def test_stein_integrand_index_protocol_on_fake_problem():
+    from gradient_free_mcmc_postprocessing_b200.integrand import SteinIntegrand
+    prob = _FakeProblem(12)
+    integ = SteinIntegrand(prob)
+    t = prob.table
+    # the three call shapes _greedy_search / ksd / kmat use (JAX_Stein_Thinning.ipynb#c17,#c22; test_ksd.py:16-20)
+    np.testing.assert_array_equal(integ(slice(None), slice(None)), np.diag(t))
+    np.testing.assert_array_equal(integ(slice(None), [5]), t[:, 5])
+    np.testing.assert_array_equal(integ(np.arange(4), [7]), t[:4, 7])
+    rows, cols = np.triu_indices(12)
+    np.testing.assert_array_equal(integ(rows, cols), t[rows, cols])
+    np.testing.assert_array_equal(integ([3], [3]), t[[3], [3]])
+    # re-indexing composes (code/src/utils/ksd.py:9-16) and is honoured by kmat / ksd
+    perm = np.array([2, 0, 4, 3, 1, 11, 7])
+    sub = reindex_integrand(integ, perm)
+    np.testing.assert_array_equal(sub(slice(None), [1]), t[perm, perm[1]])
+    np.testing.assert_array_equal(kmat(sub, 5), t[np.ix_(perm[:5], perm[:5])])
+    again = reindex_integrand(sub, np.array([6, 0, 3]))
+    np.testing.assert_array_equal(kmat(again, 3), t[np.ix_(perm[[6, 0, 3]], perm[[6, 0, 3]])])
+    assert ksd(sub, 4).shape == (4,)
+    with pytest.raises(NotImplementedError):
+        sub.thin(3)
+
+
+def test_pick_winner_matches_device_comparator_semantics():
+    """distributed.pick_winner is the host mirror of gfk::cand_better (stein_math.cuh)."""
+    from gradient_free_mcmc_postprocessing_b200.distributed import pick_winner
+    assert pick_winner([1.0, 1.0, 2.0], [9, 4, 1]) == 4            # ties -> lowest index
+    assert pick_winner([1.0, np.nan, 0.0], [0, 5, 9]) == 5         # NaN beats every number (np.argmin)
+    assert pick_winner([np.nan, np.nan], [8, 3]) == 3
+    assert pick_winner([np.inf, np.inf], [2, 1]) == 1
+    assert pick_winner([-np.inf, 0.0], [7, 0]) == 7
