@@ -47,6 +47,13 @@ __device__ __forceinline__ long long row_of(const KsdArgs<T>& a, long long t) {
 }
 
 // ---- asynchronous global -> shared copies (LDGSTS): no register staging, overlap with the FMA loop ----
+#if defined(GFK_SIMT_HOST)   // CPU emulation build of the test suite: synchronous copies
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) { *dst = *src; }
+__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) { *dst = *src; }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
@@ -58,6 +65,7 @@ __device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
 
 // stage dimensions [k0, k0 + kc) of rows [t0, t0 + TILE) into dst[k][LD] (zero padded), asynchronously.
 // Consecutive threads read consecutive k of one row (coalesced); the padded LD spreads the stores.

@@ -48,9 +48,13 @@ static_assert(offsetof(ThinWs, send) % 16 == 0 && offsetof(ThinWs, recv) % 16 ==
 
 #ifdef GFK_TRACE
 __device__ __forceinline__ long long gfk_now() {
+#if defined(GFK_SIMT_HOST)
+    return 0;
+#else
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
     return t;
+#endif
 }
 #define GFK_STAMP(step, phase) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (step) < 128) ws->trace[(step)][(phase)] = gfk_now(); } while (0)
 #define GFK_STAMP_CTA(step) do { if (threadIdx.x == 0 && (step) >= 32 && (step) < 96 && blockIdx.x < 160) ws->trace_cta[(step) - 32][blockIdx.x] = gfk_now(); } while (0)
@@ -133,6 +137,14 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     return *reinterpret_cast<const volatile unsigned*>(p);
 }
 
+// inside every spin loop on memory another CTA / rank writes: nothing on the device; the CPU emulation build of
+// the test suite (tests/host/simt) lets the other emulated threads run
+#if defined(GFK_SIMT_HOST)
+#define GFK_SPIN_HINT() simt::poll_yield()
+#else
+#define GFK_SPIN_HINT() do { } while (0)
+#endif
+
 // Intra-GPU record: (value 64 bits, index 32 bits) in TWO self-validating words, each a 16-bit tag over a
 // 48-bit payload, moved with one 16-byte vector access (each 8-byte half is single-copy atomic and carries
 // its own tag, so a torn pair is simply seen as "not there yet").  One request per slot instead of three.
@@ -141,10 +153,22 @@ __device__ __forceinline__ void slot_store(unsigned long long* p, unsigned tag16
     const unsigned long long t = (unsigned long long)(tag16 & 0xffffu) << 48;
     const unsigned long long a = t | (vb >> 16);
     const unsigned long long b = t | ((vb & 0xffffull) << 32) | (unsigned long long)i;
+#if defined(GFK_SIMT_HOST)
+    simt::check_align(p, 16, "slot_store");
+    __atomic_store_n(p, a, __ATOMIC_RELAXED);
+    __atomic_store_n(p + 1, b, __ATOMIC_RELAXED);
+#else
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+#endif
 }
 __device__ __forceinline__ void slot_load(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+#if defined(GFK_SIMT_HOST)
+    simt::check_align(p, 16, "slot_load");
+    a = __atomic_load_n(p, __ATOMIC_RELAXED);
+    b = __atomic_load_n(p + 1, __ATOMIC_RELAXED);
+#else
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+#endif
 }
 __device__ __forceinline__ bool slot_ready(unsigned long long a, unsigned long long b, unsigned tag16) {
     return (unsigned)(a >> 48) == (tag16 & 0xffffu) && (unsigned)(b >> 48) == (tag16 & 0xffffu);
@@ -190,6 +214,7 @@ __device__ __forceinline__ Cand mail_wait(const MailArgs& m, int n_ranks, int ex
             w0 = w[0]; w1 = w[1]; w2 = w[2];
             if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && (unsigned)(w2 >> 32) == tag) break;
             if (++spins > kSpinLimit || (abort_flag && ld_volatile_u32(abort_flag))) { bad = true; break; }
+            GFK_SPIN_HINT();
         }
         v = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
         i = (unsigned)(w2 & 0xffffffffull);
@@ -712,6 +737,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                             }
                         }
                         if (pending && (++spins > kSpinLimit || ld_volatile_u32(&ws->abort))) { dead = true; break; }
+                        if (pending) GFK_SPIN_HINT();
                     }
                     dead = __any_sync(0xffffffffu, dead);
                     warp_argmin(wv, wi);
@@ -734,6 +760,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                             slot_load(bc, w0, w1);
                             if (slot_ready(w0, w1, tag16)) break;
                             if (++spins > kSpinLimit || ld_volatile_u32(&ws->abort)) { dead = true; break; }
+                            GFK_SPIN_HINT();
                         }
                     }
                     dead = __any_sync(0xffffffffu, dead);
@@ -870,6 +897,31 @@ static int launch_step(const ThinArgs<T>& a, int d, cudaStream_t st, int grid_sm
 }
 
 
+// shared-memory opt-in + "does one CTA fit an SM" for a persistent kernel; cudaSuccess if it can be launched
+template <typename K>
+static cudaError_t persistent_prepare(K kernel, int threads, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); return e; }
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+    if (e != cudaSuccess || occ < 1) { cudaGetLastError(); return e != cudaSuccess ? e : cudaErrorInvalidValue; }
+    return cudaSuccess;
+}
+
+// cooperative launch (all CTAs co-resident: the kernels spin on each other's flags) with typed arguments
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cooperative(void (*kernel)(KArgs...), unsigned grid, int threads, size_t smem, cudaStream_t st,
+                                      Args... args) {
+#if defined(GFK_SIMT_HOST)
+    (void)st;
+    simt::launch(dim3(grid), dim3((unsigned)threads), smem, true, [=]() { kernel(args...); });
+    return cudaGetLastError();
+#else
+    void* params[] = {(void*)&args...};
+    return cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3((unsigned)threads), params, smem, st);
+#endif
+}
+
 // persistent path: returns 1 if it ran, 0 if not eligible, < 0 on error
 template <typename T, int D, bool STRICT>
 static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, cudaStream_t st) {
@@ -897,22 +949,13 @@ static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, c
     const char* env = getenv("GFK_RESIDENT");
     if (env && env[0] == '0') rpt_res = 0;
     const size_t smem = base + (size_t)rpt_res * per_row_slot;
-    ThinArgs<T> args = a;
-    int m_arg = m, rpt_arg = rpt, res_arg = rpt_res;
-    void* params[] = {&args, &m_arg, &rpt_arg, &res_arg};
-    const void* fn = (a.n_ranks > 1) ? (const void*)thin_persistent_kernel<T, D, STRICT, true>
-                                     : (const void*)thin_persistent_kernel<T, D, STRICT, false>;
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem) != cudaSuccess || occ < 1) {
-        cudaGetLastError();
-        return 0;
-    }
+    const bool multi = a.n_ranks > 1;
+    cudaError_t e = multi ? persistent_prepare(thin_persistent_kernel<T, D, STRICT, true>, threads, smem)
+                          : persistent_prepare(thin_persistent_kernel<T, D, STRICT, false>, threads, smem);
+    if (e != cudaSuccess) return 0;
     thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail);
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(threads), params, smem, st);
+    e = multi ? launch_cooperative(thin_persistent_kernel<T, D, STRICT, true>, (unsigned)grid, threads, smem, st, a, m, rpt, rpt_res)
+              : launch_cooperative(thin_persistent_kernel<T, D, STRICT, false>, (unsigned)grid, threads, smem, st, a, m, rpt, rpt_res);
     if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
     count_launches(2);
     return 1;

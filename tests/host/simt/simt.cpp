@@ -1,0 +1,445 @@
+// simt.cpp - fiber scheduler and fake CUDA runtime of the SIMT emulator (see simt.h).  TEST INFRASTRUCTURE ONLY.
+#include "simt.h"
+
+#include <stdarg.h>
+#include <sys/mman.h>
+
+#include <atomic>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if !defined(__x86_64__)
+#error "the SIMT emulator's context switch is written for x86-64"
+#endif
+
+// callee-saved registers + stack pointer; everything else is dead across a call by the ABI
+extern "C" void simt_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl simt_switch
+.hidden simt_switch
+.type simt_switch,@function
+simt_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size simt_switch,.-simt_switch
+)");
+
+namespace simt {
+
+constexpr size_t kStackBytes = 64 * 1024;
+enum Wait { W_NONE = 0, W_BLOCK = 1, W_WARP = 2 };
+
+struct WarpState {
+    unsigned long long buf[2][32];
+    unsigned mask[2] = {0, 0};   // lanes that took part in the collective held in buf[.]
+    unsigned gen = 0;
+    int arrived = 0;
+    int alive = 0;
+    unsigned alive_mask = 0;
+};
+
+struct Fiber {
+    ThreadCtx ctx;
+    void* sp = nullptr;
+    int wait = W_NONE;
+    unsigned wait_gen = 0;
+    bool done = false;
+    int warp = 0, lane = 0;
+    unsigned last_mask = 0;
+};
+
+struct Block {
+    std::vector<Fiber> fibers;
+    std::vector<WarpState> warps;
+    unsigned gen = 0;
+    int arrived = 0;
+    int alive = 0;
+    void* sched_sp = nullptr;
+    Fiber* running = nullptr;
+    char* smem = nullptr;
+    const std::function<void()>* fn = nullptr;
+    bool failed = false;
+    const char* site_file = nullptr;   // call site of the __syncthreads being collected
+    int site_line = 0;
+};
+
+static thread_local Block* t_blk = nullptr;
+
+// ---- errors ------------------------------------------------------------------------------------------------
+static std::mutex g_err_mu;
+static char g_err_msg[1024] = "";
+static std::atomic<int> g_last_error{0};
+static std::atomic<bool> g_abort{false};
+constexpr int kSimtLaunchFailure = 719;
+
+static void record_error(const char* msg) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    if (!g_last_error.load()) {
+        snprintf(g_err_msg, sizeof(g_err_msg), "%s", msg);
+        g_last_error.store(kSimtLaunchFailure);
+    }
+    if (getenv("SIMT_VERBOSE")) fprintf(stderr, "[simt] %s\n", msg);
+}
+
+[[noreturn]] void fail(const char* fmt, ...) {
+    char buf[900];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    Block* b = t_blk;
+    if (!b || !b->running) {
+        fprintf(stderr, "[simt] fatal outside a kernel: %s\n", buf);
+        abort();
+    }
+    char where[1024];
+    const ThreadCtx& c = b->running->ctx;
+    snprintf(where, sizeof(where), "%s (block %u, thread %u)", buf, c.bid.x, c.tid.x);
+    record_error(where);
+    g_abort.store(true);
+    b->failed = true;
+    simt_switch(&b->running->sp, b->sched_sp);   // the scheduler abandons this block
+    abort();
+}
+
+void check_align(const void* p, size_t a, const char* what) {
+    if (a > 1 && (reinterpret_cast<uintptr_t>(p) % a) != 0) fail("misaligned address in %s: %p needs %zu-byte alignment", what, p, a);
+}
+
+ThreadCtx* cur() { return &t_blk->running->ctx; }
+void* dyn_smem() { return t_blk->smem; }
+
+static inline void yield_to_scheduler(Block* b, Fiber* f) { simt_switch(&f->sp, b->sched_sp); }
+
+static int g_random_sched = -1;
+static unsigned g_seed = 1;
+static bool random_sched() {
+    if (g_random_sched < 0) {
+        const char* e = getenv("SIMT_SCHED");
+        g_random_sched = (e && strncmp(e, "random", 6) == 0) ? 1 : 0;
+        if (g_random_sched && e[6] == ':') g_seed = (unsigned)strtoul(e + 7, nullptr, 10);
+    }
+    return g_random_sched == 1;
+}
+
+void syncthreads(const char* file, int line) {
+    Block* b = t_blk;
+    Fiber* f = b->running;
+    const unsigned g = b->gen;
+    if (b->arrived == 0) {
+        b->site_file = file;
+        b->site_line = line;
+    } else if (b->site_line != line || b->site_file != file) {
+        fail("divergent __syncthreads: threads of one block wait at %s:%d and at %s:%d", b->site_file, b->site_line,
+             file, line);
+    }
+    if (++b->arrived == b->alive) {
+        b->arrived = 0;
+        b->gen++;
+        if (random_sched()) { f->wait = W_NONE; yield_to_scheduler(b, f); }
+        return;
+    }
+    f->wait = W_BLOCK;
+    f->wait_gen = g;
+    yield_to_scheduler(b, f);
+}
+
+const unsigned long long* warp_gather(unsigned long long bits) {
+    Block* b = t_blk;
+    Fiber* f = b->running;
+    WarpState& w = b->warps[f->warp];
+    const unsigned g = w.gen;
+    w.buf[g & 1][f->lane] = bits;
+    if (++w.arrived == w.alive) {
+        w.arrived = 0;
+        w.mask[g & 1] = w.alive_mask;
+        w.gen++;
+        if (random_sched()) { f->wait = W_NONE; yield_to_scheduler(b, f); }
+    } else {
+        f->wait = W_WARP;
+        f->wait_gen = g;
+        yield_to_scheduler(b, f);
+    }
+    f->last_mask = w.mask[g & 1];
+    return w.buf[g & 1];
+}
+
+// the lanes that took part in this thread's most recent collective (lanes that exit later must still count)
+unsigned warp_alive_mask() { return t_blk->running->last_mask; }
+
+void poll_yield() {
+    Block* b = t_blk;
+    if (!b || !b->running) return;
+    if (g_abort.load(std::memory_order_relaxed)) fail("abandoned: another block of the launch failed");
+    Fiber* f = b->running;
+    f->wait = W_NONE;
+    yield_to_scheduler(b, f);
+}
+
+static void fiber_main() {
+    Block* b = t_blk;
+    (*b->fn)();
+    Fiber* f = b->running;
+    f->done = true;
+    WarpState& w = b->warps[f->warp];
+    b->alive--;
+    w.alive--;
+    w.alive_mask &= ~(1u << f->lane);
+    // threads that exit no longer take part in barriers
+    if (b->alive > 0 && b->arrived == b->alive) { b->arrived = 0; b->gen++; }
+    if (w.alive > 0 && w.arrived == w.alive) { w.arrived = 0; w.mask[w.gen & 1] = w.alive_mask; w.gen++; }
+    simt_switch(&f->sp, b->sched_sp);
+    abort();
+}
+
+// ---- stacks ------------------------------------------------------------------------------------------------
+static std::mutex g_stack_mu;
+static std::vector<std::pair<size_t, char*>> g_stack_pool;
+
+static char* stacks_acquire(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_stack_mu);
+        for (size_t i = 0; i < g_stack_pool.size(); ++i) {
+            if (g_stack_pool[i].first == bytes) {
+                char* p = g_stack_pool[i].second;
+                g_stack_pool.erase(g_stack_pool.begin() + (long)i);
+                return p;
+            }
+        }
+    }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (p == MAP_FAILED) { fprintf(stderr, "[simt] cannot map %zu bytes of fiber stacks\n", bytes); abort(); }
+    return static_cast<char*>(p);
+}
+static void stacks_release(size_t bytes, char* p) {
+    std::lock_guard<std::mutex> lk(g_stack_mu);
+    if (g_stack_pool.size() < 64) g_stack_pool.emplace_back(bytes, p);
+    else munmap(p, bytes);
+}
+
+static inline bool runnable(const Block& b, const Fiber& f) {
+    if (f.done) return false;
+    if (f.wait == W_NONE) return true;
+    if (f.wait == W_BLOCK) return b.gen != f.wait_gen;
+    return b.warps[f.warp].gen != f.wait_gen;
+}
+
+static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, dim3 block, size_t smem_bytes) {
+    const int T = (int)(block.x * block.y * block.z);
+    const int nwarps = (T + 31) / 32;
+    b.gen = 0;
+    b.arrived = 0;
+    b.alive = T;
+    b.failed = false;
+    b.warps.assign((size_t)nwarps, WarpState());
+    if (smem_bytes) memset(b.smem, 0xff, smem_bytes);   // poison: NaN patterns / huge integers
+    uint3 bid;
+    bid.x = linear_block % grid.x;
+    bid.y = (linear_block / grid.x) % grid.y;
+    bid.z = linear_block / (grid.x * grid.y);
+    for (int t = 0; t < T; ++t) {
+        Fiber& f = b.fibers[(size_t)t];
+        f.ctx.tid.x = (unsigned)t % block.x;
+        f.ctx.tid.y = ((unsigned)t / block.x) % block.y;
+        f.ctx.tid.z = (unsigned)t / (block.x * block.y);
+        f.ctx.bid = bid;
+        f.ctx.bdim = uint3{block.x, block.y, block.z};
+        f.ctx.gdim = uint3{grid.x, grid.y, grid.z};
+        f.wait = W_NONE;
+        f.done = false;
+        f.warp = t / 32;
+        f.lane = t % 32;
+        WarpState& w = b.warps[(size_t)f.warp];
+        w.alive++;
+        w.alive_mask |= 1u << f.lane;
+        void** top = reinterpret_cast<void**>(stacks + (size_t)(t + 1) * kStackBytes - 64);
+        for (int r = 0; r < 6; ++r) top[r] = nullptr;
+        top[6] = reinterpret_cast<void*>(&fiber_main);
+        top[7] = nullptr;
+        f.sp = top;
+    }
+    const bool rnd = random_sched();
+    unsigned rng = g_seed * 2654435761u + linear_block * 40503u + 12345u;
+    int next = 0;
+    std::vector<int> cand;
+    while (b.alive > 0 && !b.failed) {
+        int pick = -1;
+        if (!rnd) {
+            for (int k = 0; k < T; ++k) {
+                const int i = (next + k) % T;
+                if (runnable(b, b.fibers[(size_t)i])) { pick = i; break; }
+            }
+        } else {
+            cand.clear();
+            for (int i = 0; i < T; ++i)
+                if (runnable(b, b.fibers[(size_t)i])) cand.push_back(i);
+            if (!cand.empty()) {
+                rng = rng * 1664525u + 1013904223u;
+                pick = cand[(rng >> 8) % cand.size()];
+            }
+        }
+        if (pick < 0) {
+            int at_block = 0, at_warp = 0;
+            for (const Fiber& f : b.fibers) {
+                if (f.done) continue;
+                if (f.wait == W_BLOCK) ++at_block; else if (f.wait == W_WARP) ++at_warp;
+            }
+            char msg[256];
+            snprintf(msg, sizeof(msg),
+                     "deadlock in block %u: %d threads alive, %d wait in __syncthreads, %d in a warp collective "
+                     "(divergent barrier?)", linear_block, b.alive, at_block, at_warp);
+            record_error(msg);
+            g_abort.store(true);
+            b.failed = true;
+            break;
+        }
+        next = pick + 1;
+        Fiber& f = b.fibers[(size_t)pick];
+        f.wait = W_NONE;
+        b.running = &f;
+        simt_switch(&b.sched_sp, f.sp);
+        b.running = nullptr;
+    }
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
+void launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& fn) {
+    const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+    const int T = (int)(block.x * block.y * block.z);
+    if (nblocks == 0 || T <= 0 || T > 1024) { record_error("invalid launch configuration"); return; }
+    if (smem > 227 * 1024) { record_error("too much dynamic shared memory"); return; }
+    if (t_blk && t_blk->running) { record_error("nested launch"); return; }
+    g_abort.store(false);
+    const size_t stack_bytes = (size_t)T * kStackBytes;
+    std::atomic<size_t> next_block{0};
+    auto worker = [&](bool one_block_only, size_t fixed_block) {
+        Block b;
+        b.fibers.resize((size_t)T);
+        b.fn = &fn;
+        char* stacks = stacks_acquire(stack_bytes);
+        b.smem = smem ? static_cast<char*>(aligned_alloc(128, (smem + 127) / 128 * 128)) : nullptr;
+        t_blk = &b;
+        if (one_block_only) {
+            run_block(b, stacks, (unsigned)fixed_block, grid, block, smem);
+        } else {
+            for (;;) {
+                const size_t i = next_block.fetch_add(1);
+                if (i >= nblocks || g_abort.load()) break;
+                run_block(b, stacks, (unsigned)i, grid, block, smem);
+            }
+        }
+        t_blk = nullptr;
+        free(b.smem);
+        stacks_release(stack_bytes, stacks);
+    };
+    if (cooperative) {
+        if (nblocks > 256) { record_error("cooperative launch too large for the emulator"); return; }
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < nblocks; ++i) th.emplace_back(worker, true, i);
+        for (auto& t : th) t.join();
+        return;
+    }
+    int P = env_int("SIMT_WORKERS", 0);
+    if (P <= 0) {
+        P = (int)std::thread::hardware_concurrency();
+        if (P > 8) P = 8;
+        if (P < 1) P = 1;
+    }
+    if ((size_t)P > nblocks) P = (int)nblocks;
+    if (P == 1) {
+        worker(false, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int i = 0; i < P; ++i) th.emplace_back(worker, false, (size_t)0);
+    for (auto& t : th) t.join();
+}
+
+}  // namespace simt
+
+// test control: scheduling order of the emulated threads (0 round-robin, 1 random with `seed`)
+extern "C" void simt_set_schedule(int random, unsigned seed) {
+    simt::g_random_sched = random ? 1 : 0;
+    simt::g_seed = seed;
+}
+
+// ---- fake CUDA runtime -----------------------------------------------------------------------------------------
+const char* cudaGetErrorString(cudaError_t e) {
+    if (e == simt::kSimtLaunchFailure) return simt::g_err_msg;
+    switch (e) {
+        case cudaSuccess: return "no error";
+        case cudaErrorInvalidValue: return "invalid argument";
+        case cudaErrorMemoryAllocation: return "out of memory";
+        case cudaErrorNotSupported: return "operation not supported (SIMT emulator)";
+        default: return "unknown error";
+    }
+}
+cudaError_t cudaGetLastError() { return simt::g_last_error.exchange(0); }
+cudaError_t cudaGetDevice(int* dev) { *dev = 0; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
+    switch (a) {
+        case cudaDevAttrMultiProcessorCount: *v = simt::env_int("SIMT_SMS", 4); return cudaSuccess;
+        case cudaDevAttrCooperativeLaunch: *v = 1; return cudaSuccess;
+        case cudaDevAttrMaxSharedMemoryPerBlockOptin: *v = 227 * 1024; return cudaSuccess;
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+    memset(p, 0, sizeof(*p));
+    snprintf(p->name, sizeof(p->name), "SIMT host emulator");
+    p->major = 10;
+    p->minor = 0;
+    p->multiProcessorCount = simt::env_int("SIMT_SMS", 4);
+    return cudaSuccess;
+}
+cudaError_t cudaMalloc(void** p, size_t bytes) {
+    *p = aligned_alloc(256, (bytes + 255) / 256 * 256);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { memcpy(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) {
+    memcpy(dst, src, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaMemset(void* p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return simt::g_last_error.load(); }
+cudaError_t cudaDeviceSynchronize() { return simt::g_last_error.load(); }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new SimtEvent{0.0}; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+    e->t_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+cudaError_t simt_func_set_attribute(size_t bytes) { return bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t simt_occupancy(int* blocks, int threads, size_t smem) {
+    *blocks = (threads <= 1024 && smem <= 227 * 1024) ? 1 : 0;
+    return cudaSuccess;
+}

@@ -1,0 +1,407 @@
+"""The REAL kernel sources of libgfk (csrc/*.cu) executed on the CPU by the SIMT emulator in tests/host/simt and
+compared with the oracle - the same parity cases as tests/test_gpu_parity.py at sizes a CPU finishes in seconds.
+
+This is test infrastructure: it proves the kernels' logic (index arithmetic, shared-memory layouts, barriers, warp /
+block / grid reductions, tie-breaking, the flag-in-data grid exchange of the single-launch kernel) without a GPU.  It
+says nothing about device arithmetic that differs from the host's (CUDA's exp / rsqrt), which the `-m gpu` tests
+cover.  With the host's exact reciprocal square root the strict mode must reproduce the oracle's indices exactly.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import simt_harness as H
+from oracle.stein_thinning_oracle import kernel as ok, stein as os_, thinning as ot
+
+
+def _mcmc_like(rng, n, d, dup=0.5):
+    base = rng.standard_normal((n, d)) @ (np.eye(d) + 0.3 * rng.standard_normal((d, d)))
+    keep = rng.random(n) > dup
+    keep[0] = True
+    src = np.maximum.accumulate(np.where(keep, np.arange(n), 0))
+    x = base[src]
+    grad = -(x - 0.1) * (1.0 + 0.2 * np.arange(d))
+    return np.ascontiguousarray(x), np.ascontiguousarray(grad)
+
+
+@pytest.fixture(autouse=True)
+def _clean_env(monkeypatch):
+    for k in ('GFK_PERSISTENT', 'GFK_RESIDENT', 'SIMT_SMS', 'SIMT_WORKERS'):
+        monkeypatch.delenv(k, raising=False)
+    H.load()
+    H.set_schedule(False)
+    yield
+    H.set_schedule(False)
+
+
+STRATEGIES = {
+    'single-launch': {},
+    'single-launch-rows-from-global': {'GFK_RESIDENT': '0'},
+    'launch-per-step': {'GFK_PERSISTENT': '0'},
+}
+
+
+# ---- golden vectors through the emulated kernels -----------------------------------------------------------
+@pytest.mark.parametrize('strategy', list(STRATEGIES))
+@pytest.mark.parametrize('precision', ['f64', 'f64-fast'])
+def test_golden_g1_g2_g3(g13, strategy, precision, monkeypatch):
+    for k, v in STRATEGIES[strategy].items():
+        monkeypatch.setenv(k, v)
+    idx, _ = H.SimProblem(g13['sample'], g13['gradient'], precision=precision).thin(20)
+    assert np.array_equal(idx, g13['idx_thin'])
+    idx, _ = H.SimProblem(g13['sample'], g13['gradient'], g13['log_p'], g13['log_p'], precision=precision).thin(20)
+    assert np.array_equal(idx, g13['idx_thin'])
+    idx, _ = H.SimProblem(g13['sample'], g13['gradient_q'], g13['log_p'], g13['log_q'], precision=precision).thin(20)
+    assert np.array_equal(idx, g13['idx_thin_gf'])
+
+
+def test_golden_g4_g5(g45):
+    idx, _ = H.SimProblem(g45['sample'], g45['gradient'], preconditioner='med').thin(1000)
+    assert len(np.unique(idx)) == 538
+    idx, _ = H.SimProblem(g45['sample'], g45['gradient_q'], g45['log_p'], g45['log_q'], preconditioner='med').thin(1000)
+    assert len(np.unique(idx)) == 400
+    p = H.SimProblem(g45['sample'], g45['gradient_q_laplace'], g45['log_p'], g45['log_q_laplace'], preconditioner='med')
+    assert p.spread > 10                                     # the caller's UserWarning condition
+    idx, _ = p.thin(1500)
+    assert np.array_equal(np.unique(idx), [494])
+
+
+# ---- greedy search: every kernel variant against the oracle ----------------------------------------------------
+@pytest.mark.parametrize('d', [1, 2, 3, 4])
+@pytest.mark.parametrize('sms', [1, 3, 7])
+def test_single_launch_kernel_matches_oracle(d, sms, monkeypatch):
+    """thin_persistent_kernel: 1, 3 and 7 concurrently running CTAs, partly filled last CTA, rows per thread > 1."""
+    monkeypatch.setenv('SIMT_SMS', str(sms))
+    rng = np.random.default_rng(100 + d)
+    n = 2500 + 37 * d
+    x, g = _mcmc_like(rng, n, d)
+    log_p = -0.5 * np.sum(x ** 2, axis=1) + 0.3 * np.sin(x[:, 0])
+    log_q = -0.5 * np.sum((x - 0.1) ** 2, axis=1) / 1.3
+    m = 40
+    expect = ot.thin(x, g, m, preconditioner='med')
+    expect_gf = ot.thin_gf(x, log_p, log_q, g, m, preconditioner='med')
+    for precision in ('f64', 'f64-fast'):
+        idx, _ = H.SimProblem(x, g, preconditioner='med', precision=precision).thin(m)
+        assert np.array_equal(idx, expect), (precision, np.flatnonzero(idx != expect)[:3])
+        idx, _ = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(m)
+        assert np.array_equal(idx, expect_gf), (precision, np.flatnonzero(idx != expect_gf)[:3])
+
+
+@pytest.mark.parametrize('d', [1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 33, 64, 130])
+def test_launch_per_step_kernels_match_oracle(d, monkeypatch):
+    """thin_step_small_kernel (d <= 4), thin_step_chunked_kernel (d <= 128), thin_step_tiled_kernel (strict d > 128),
+    thin_init_kernel, the last-block-done grid argmin and thin_finish_kernel."""
+    monkeypatch.setenv('GFK_PERSISTENT', '0')
+    rng = np.random.default_rng(1000 + d)
+    x, g = _mcmc_like(rng, 1300, d)
+    m = 25
+    for pre in ('id', 'med'):
+        expect = ot.thin(x, g, m, preconditioner=pre)
+        for precision in ('f64', 'f64-fast'):
+            idx, _ = H.SimProblem(x, g, preconditioner=pre, precision=precision).thin(m)
+            assert np.array_equal(idx, expect), (precision, d, pre, np.flatnonzero(idx != expect)[:3])
+
+
+@pytest.mark.parametrize('range_cap', [None, 5.0])
+@pytest.mark.parametrize('d', [2, 10])
+def test_gradient_free_with_range_cap(d, range_cap):
+    rng = np.random.default_rng(2000 + d)
+    x, gq = _mcmc_like(rng, 1500, d)
+    log_p = -0.5 * np.sum(x ** 2, axis=1) + 0.3 * np.sin(x[:, 0])
+    log_q = -0.5 * np.sum((x - 0.1) ** 2, axis=1) / 1.3
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        expect = ot.thin_gf(x, log_p, log_q, gq, 30, preconditioner='med', range_cap=range_cap)
+    for precision in ('f64', 'f64-fast'):
+        idx, _ = H.SimProblem(x, gq, log_p, log_q, preconditioner='med', range_cap=range_cap, precision=precision).thin(30)
+        assert np.array_equal(idx, expect), (precision, d, range_cap)
+
+
+@pytest.mark.parametrize('d', [2, 3, 4])
+def test_launch_strategies_agree_bitwise(d, monkeypatch):
+    """Same indices AND the same final running objective, bit for bit, from all three launch strategies."""
+    rng = np.random.default_rng(500 + d)
+    x, g = _mcmc_like(rng, 3001, d)
+    log_p = -0.5 * np.sum(x ** 2, axis=1)
+    log_q = log_p / 1.1
+    for precision in ('f64', 'f64-fast', 'f32'):
+        results = []
+        for env in STRATEGIES.values():
+            for k in ('GFK_PERSISTENT', 'GFK_RESIDENT'):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            results.append(H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(60))
+        for idx, obj in results[1:]:
+            assert np.array_equal(idx, results[0][0]), precision
+            assert np.array_equal(obj, results[0][1]), precision
+
+
+def test_final_objective_is_numpys_bit_for_bit():
+    """Without standardisation (its column sums are reduced in a different order) the strict kernels must leave
+    exactly the running objective numpy computes, wherever numpy's pow is correctly rounded - demand 90 % equal
+    and the rest within 4 ulp-ish."""
+    rng = np.random.default_rng(9)
+    x, g = _mcmc_like(rng, 2000, 3, dup=0.3)
+    integrand = ot._make_stein_integrand(x, g, standardize=False)
+    m = 15
+    expect = ot._greedy_search(m, integrand)
+    a = integrand(slice(None), slice(None)).copy()
+    for j in expect[:-1]:
+        a += 2 * integrand(slice(None), [j])
+    idx, obj = H.SimProblem(x, g, standardize=False).thin(m)
+    assert np.array_equal(idx, expect)
+    assert np.mean(obj == a) > 0.9
+    np.testing.assert_allclose(obj, a, rtol=1e-14)
+
+
+def test_selection_with_replacement_and_row_shards(monkeypatch):
+    rng = np.random.default_rng(5)
+    x, g = _mcmc_like(rng, 40, 2, dup=0.0)
+    expect = ot.thin(x, g, 300)
+    for env in STRATEGIES.values():
+        for k in ('GFK_PERSISTENT', 'GFK_RESIDENT'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        idx, _ = H.SimProblem(x, g).thin(300)
+        assert np.array_equal(idx, expect)
+    # a rank's shard [r0, r1) alone: greedy search restricted to those candidate rows (global indices)
+    x, g = _mcmc_like(rng, 900, 3)
+    p = H.SimProblem(x, g, standardize=False)
+    integrand = ot._make_stein_integrand(x, g, standardize=False)
+    r0, r1 = 311, 777
+    a = integrand(slice(None), slice(None))[r0:r1].copy()
+    want = []
+    for _ in range(12):
+        j = r0 + int(np.argmin(a))
+        want.append(j)
+        a += 2 * integrand(np.arange(r0, r1), [j])
+    idx, _ = p.thin(12, row_range=(r0, r1))
+    assert np.array_equal(idx, want)
+
+
+def test_nan_objective_is_selected_first_like_numpy(monkeypatch):
+    """np.argmin returns the first NaN; an inf - inf in the weights produces one."""
+    rng = np.random.default_rng(3)
+    x, g = _mcmc_like(rng, 600, 2, dup=0.0)
+    g[417] = 1e200      # overflow to inf in <sx, sy>, inf - inf -> NaN downstream
+    g[88] = 1e200
+    with np.errstate(all='ignore'):
+        expect = ot.thin(x, g, 5, standardize=False)
+    for env in ({}, {'GFK_PERSISTENT': '0'}):
+        monkeypatch.delenv('GFK_PERSISTENT', raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        idx, _ = H.SimProblem(x, g, standardize=False).thin(5)
+        assert np.array_equal(idx, expect)
+
+
+# ---- kernel values, Gram matrix, KSD ---------------------------------------------------------------------------
+@pytest.mark.parametrize('gf', [False, True])
+@pytest.mark.parametrize('d', [1, 2, 7, 10, 33, 70])
+def test_ksd_rowsum_kernel_matches_oracle(gf, d):
+    """ksd_rowsum_kernel (tile staging, the 4 x 4 register blocks with strided columns, triangular mask, row
+    reduction), ksd_diag_kernel and the sequential scan - m not a multiple of the tile, several dimension chunks."""
+    rng = np.random.default_rng(4000 + d)
+    n = 333
+    x, g = _mcmc_like(rng, n, d, dup=0.1)
+    if gf:
+        log_p = -0.5 * np.sum(x ** 2, axis=1)
+        log_q = log_p + 2.0 * np.sin(x[:, 0]) - 0.1 * x[:, -1] ** 2       # weights within float32 range for any d
+        ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med')
+        mk = lambda prec: H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=prec)   # noqa: E731
+    else:
+        ref = ot._make_stein_integrand(x, g, preconditioner='med')
+        mk = lambda prec: H.SimProblem(x, g, preconditioner='med', precision=prec)                 # noqa: E731
+    km_ref = os_.kmat(ref, n)
+    ks_ref = os_.ksd(ref, n)
+    low_ref = np.array([km_ref[t, :t].sum() for t in range(n)])
+    scale = np.abs(km_ref) + 1e-3 * np.abs(km_ref).max()
+    for prec, tol_k, tol_ks in (('f64', 1e-11, 1e-10), ('f64-fast', 1e-11, 1e-10), ('f32', 5e-4, 1e-5)):
+        p = mk(prec)
+        km = p.kmat()
+        assert np.max(np.abs(km - km_ref) / scale) < tol_k, prec
+        low, diag = p.ksd_rowsums()
+        np.testing.assert_allclose(diag, np.diag(km_ref), rtol=tol_k * 10, err_msg=prec)
+        assert np.max(np.abs(low - low_ref)) <= tol_ks * np.abs(km_ref).sum(), prec
+        np.testing.assert_allclose(p.ksd(), ks_ref, rtol=tol_ks, atol=0, err_msg=prec)
+    # selections with repeats, split over 1, 2 and 3 ranks
+    sel = rng.integers(0, n, 150)
+    want = os_.ksd(lambda a, b: ref(sel[a], sel[b]), 150)
+    p = mk('f64')
+    for n_parts in (1, 2, 3):
+        np.testing.assert_allclose(p.ksd(sel=sel, n_parts=n_parts), want, rtol=1e-10, err_msg=str(n_parts))
+    parts = [p.ksd_rowsums(sel=sel, part=r, n_parts=3) for r in range(3)]
+    owners = (np.arange(150) // 64) % 3
+    for r, (low, diag) in enumerate(parts):
+        assert np.all(low[owners != r] == 0) and np.all(diag[owners != r] == 0)
+
+
+def test_ksd_dense_preconditioner_and_pairs():
+    rng = np.random.default_rng(77)
+    n, d = 200, 5
+    x, g = _mcmc_like(rng, n, d, dup=0.0)
+    a = rng.standard_normal((d, d))
+    dense = a @ a.T / d + np.eye(d)
+    s, gs = ot._validate_and_standardize(x, g, True)
+    want = lambda i, j: ok.vfk0_imq(s[i], s[j], gs[i], gs[j], dense)   # noqa: E731
+    p = H.SimProblem(x, g, preconditioner=dense, precision='f64-fast')
+    ia, ib = rng.integers(0, n, 700), rng.integers(0, n, 700)
+    np.testing.assert_allclose(p.pairs(ia, ib), want(ia, ib), rtol=1e-9, atol=1e-12)
+    km = np.array([want(np.full(n, i), np.arange(n)) for i in range(n)])
+    np.testing.assert_allclose(p.ksd(), os_.ksd(lambda i, j: km[i, j], n), rtol=1e-10)
+    idx, _ = p.thin(10)                                    # chunked kernel, DENSE instantiation
+    a_run = np.diag(km).copy()
+    expect = []
+    for _ in range(10):
+        j = int(np.argmin(a_run))
+        expect.append(j)
+        a_run += 2 * km[:, j]
+    assert np.array_equal(idx, expect)
+
+
+@pytest.mark.parametrize('d', [2, 4, 10, 64, 200])
+def test_pair_values_match_oracle(d):
+    rng = np.random.default_rng(3000 + d)
+    x, g = _mcmc_like(rng, 500, d, dup=0.2)
+    ia, ib = rng.integers(0, 500, 2000), rng.integers(0, 500, 2000)
+    raw_ref = ot._make_stein_integrand(x, g, standardize=False, preconditioner='med')(ia, ib)
+    raw = H.SimProblem(x, g, standardize=False, preconditioner='med').pairs(ia, ib)
+    assert np.mean(raw == raw_ref) > 0.85
+    assert np.max(np.abs(raw - raw_ref) / (np.abs(raw_ref) + 1e-3 * np.abs(raw_ref).max())) < 1e-13
+    want = ot._make_stein_integrand(x, g, preconditioner='med')(ia, ib)
+    scale = np.abs(want) + 1e-3 * np.abs(want).max()
+    assert np.max(np.abs(H.SimProblem(x, g, preconditioner='med', precision='f64-fast').pairs(ia, ib) - want) / scale) < 1e-11
+    assert np.max(np.abs(H.SimProblem(x, g, preconditioner='med', precision='f32').pairs(ia, ib) - want) / scale) < 2e-4
+
+
+# ---- the passes in front of the pair kernels ----------------------------------------------------------------------
+def test_standardise_median_and_log_weights():
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((5000, 6)) * np.array([1, 10, 0.1, 3, 1e-3, 50.]) + 7
+    g = rng.standard_normal((5000, 6))
+    s_ref, g_ref = ot._validate_and_standardize(x, g, True)
+    p = H.SimProblem(x, g, preconditioner='med')
+    np.testing.assert_allclose(p.x, s_ref, rtol=1e-11)
+    np.testing.assert_allclose(p.s, g_ref, rtol=1e-11)
+    # the median heuristic itself is exact: same subsample rule, scipy's operation order, exact order statistics
+    for n in (4321, 1000, 1001, 700, 2, 3):
+        y = np.ascontiguousarray(rng.standard_normal((n, 5)))
+        q = H.SimProblem(y, y, standardize=False, preconditioner='med')
+        assert np.array_equal(q.linv, ok.make_precon(y, 'med')), n
+    q = H.SimProblem(x[:, :3], g[:, :3], standardize=False, preconditioner='sclmed')
+    assert np.array_equal(q.linv, ok.make_precon(x[:, :3], 'sclmed'))
+    # log-weights and the range cap
+    log_p, log_q = rng.standard_normal(5000) * 30, rng.standard_normal(5000) * 30
+    q = H.SimProblem(x, g, log_p, log_q)
+    assert np.array_equal(q.lw, log_q - log_p) and q.spread == np.ptp(log_q - log_p)
+    q = H.SimProblem(x, g, log_p, log_q, range_cap=20.0)
+    lw = log_q - log_p
+    assert np.array_equal(q.lw, np.maximum(lw - lw.max(), -20.0))
+
+
+def test_validation_errors_surface_from_the_kernels():
+    rng = np.random.default_rng(12)
+    x, g = rng.standard_normal((50, 2)), rng.standard_normal((50, 2))
+    bad = x.copy(); bad[7, 1] = np.nan
+    with pytest.raises(H.SimError, match='NaNs or infs'):
+        H.SimProblem(bad, g)
+    badg = g.copy(); badg[3, 0] = np.inf
+    with pytest.raises(H.SimError, match='NaNs or infs'):
+        H.SimProblem(x, badg)
+    with pytest.raises(H.SimError, match='Too few unique samples'):
+        H.SimProblem(np.ones((10, 2)), np.ones((10, 2)))
+    lp = np.zeros(50); lp[4] = np.nan
+    with pytest.raises(H.SimError, match='NaNs'):
+        H.SimProblem(x, g, lp, np.zeros(50))
+
+
+def test_gaussian_proxy_kernel_matches_scipy():
+    """SURVEY 8f-1 (code/src/thinning.py:15-16): log q and grad log q of the Gaussian proxy."""
+    import ctypes
+    from scipy.stats import multivariate_normal as mvn
+    lib = H.load()
+    rng = np.random.default_rng(21)
+    for d in (1, 2, 4, 9):
+        n = 1111
+        x = np.ascontiguousarray(rng.standard_normal((n, d)) * 2 + 1)
+        a = rng.standard_normal((d, d))
+        cov = a @ a.T + np.eye(d)
+        mean = rng.standard_normal(d)
+        prec = np.linalg.inv(cov)
+        cst = d * np.log(2 * np.pi) + np.linalg.slogdet(cov)[1]
+        xd, md, pd_ = H.dev(x), H.dev(mean), H.dev(prec)
+        log_q, grad_q = H.guarded((n,), np.float64, fill=np.nan), H.guarded((n, d), np.float64, fill=np.nan)
+        H.check(lib.gfk_gaussian_proxy(H.ptr(xd), n, d, H.ptr(md), H.ptr(pd_), ctypes.c_double(cst), H.ptr(log_q),
+                                       H.ptr(grad_q), None))
+        np.testing.assert_allclose(log_q, mvn.logpdf(x, mean=mean, cov=cov), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(grad_q, -np.einsum('ij,kj->ki', prec, x - mean), rtol=1e-12, atol=1e-12)
+
+
+# ---- scheduling-order independence (a missing barrier shows up as a wrong result) -----------------------------------
+@pytest.mark.parametrize('seed', [1, 2, 3])
+def test_results_do_not_depend_on_thread_schedule(seed, monkeypatch):
+    rng = np.random.default_rng(600)
+    x, g = _mcmc_like(rng, 1200, 4)
+    log_p = -0.5 * np.sum(x ** 2, axis=1)
+    log_q = log_p / 1.2
+    base = {}
+    for strategy, env in STRATEGIES.items():
+        for k in ('GFK_PERSISTENT', 'GFK_RESIDENT'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        H.set_schedule(False)
+        p = H.SimProblem(x, g, log_p, log_q, preconditioner='med')
+        base[strategy] = p.thin(12)
+        H.set_schedule(True, seed)
+        q = H.SimProblem(x, g, log_p, log_q, preconditioner='med')
+        assert q.lam == p.lam and np.array_equal(q.x, p.x) and np.array_equal(q.lw, p.lw)
+        idx, obj = q.thin(12)
+        assert np.array_equal(idx, base[strategy][0]) and np.array_equal(obj, base[strategy][1]), strategy
+    H.set_schedule(False)
+    x, g = _mcmc_like(rng, 300, 40)
+    monkeypatch.setenv('GFK_PERSISTENT', '0')
+    p = H.SimProblem(x, g, preconditioner='med', precision='f64-fast')
+    want_idx, want_ks, want_km = p.thin(6)[0], p.ksd(), p.kmat()
+    H.set_schedule(True, seed)
+    assert np.array_equal(p.thin(6)[0], want_idx)
+    assert np.array_equal(p.ksd(), want_ks) and np.array_equal(p.kmat(), want_km)
+
+
+# ---- the emulator itself: the defects it exists to catch are reported, not silently tolerated ---------------------
+def test_emulator_reports_deliberate_defects():
+    import ctypes
+    lib = H.load()
+    lib.simt_selftest_error.restype = ctypes.c_char_p
+    rc = lib.simt_selftest_divergent_barrier()
+    assert rc != 0 and b'divergent __syncthreads' in lib.simt_selftest_error(rc)
+    rc = lib.simt_selftest_misaligned()
+    assert rc != 0 and b'misaligned address' in lib.simt_selftest_error(rc)
+    blocks, T = 3, 128
+    want = np.array([[((t + 1) % T) * 3 + b for t in range(T)] for b in range(blocks)], dtype=np.int32).reshape(-1)
+    out = np.zeros(blocks * T, dtype=np.int32)
+    P = ctypes.POINTER(ctypes.c_int)
+    for seed in (1, 2, 3):
+        H.set_schedule(True, seed)
+        assert lib.simt_selftest_neighbour(out.ctypes.data_as(P), blocks, 1) == 0
+        assert np.array_equal(out, want)                                  # with the barrier: any schedule
+    wrong = 0
+    for seed in (1, 2, 3):
+        H.set_schedule(True, seed)
+        out[:] = -1
+        assert lib.simt_selftest_neighbour(out.ctypes.data_as(P), blocks, 0) == 0
+        wrong += int(not np.array_equal(out, want))
+    assert wrong == 3                                                     # without it: caught under every seed
+    H.set_schedule(False)
+    for n in (64, 40, 33, 7):
+        out = np.full(64, -1, dtype=np.int32)
+        assert lib.simt_selftest_early_exit(out.ctypes.data_as(P), n) == 0
+        for w in range(2):
+            lanes = [t for t in range(32 * w, 32 * w + 32) if t < n]
+            mask = sum(1 << (t % 32) for t in lanes)
+            assert np.all(out[lanes].view(np.uint32) == mask), (n, w)
+        assert np.all(out[n:] == -1)
