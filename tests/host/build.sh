@@ -30,5 +30,6 @@ g++ -std=c++17 -O2 -g -fPIC -DGFK_SIMT_HOST=1 -Wno-unknown-pragmas -I"${here}/si
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 for f in api comm prep thin ksd ${GFK_SIM_EXTRA_UNITS:-} simt selftest; do [ -f "${gen}/${f}.o" ] && objs+=("${gen}/${f}.o"); done
-g++ -shared -o "${here}/libgfk_sim.so" "${objs[@]}" -ldl -lpthread
+g++ -shared -o "${here}/libgfk_sim.so" "${objs[@]}" -ldl -lpthread -lrt
+g++ -std=c++17 -O2 -g -fPIC -shared -o "${here}/libfake_nccl.so" "${here}/simt/fake_nccl.cpp" -lrt -lpthread
 echo "built ${here}/libgfk_sim.so"

@@ -1,8 +1,12 @@
 // simt.cpp - fiber scheduler and fake CUDA runtime of the SIMT emulator (see simt.h).  TEST INFRASTRUCTURE ONLY.
 #include "simt.h"
 
+#include <fcntl.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <chrono>
@@ -76,6 +80,7 @@ struct Block {
     char* smem = nullptr;
     const std::function<void()>* fn = nullptr;
     bool failed = false;
+    unsigned polls = 0;
     const char* site_file = nullptr;   // call site of the __syncthreads being collected
     int site_line = 0;
 };
@@ -190,6 +195,7 @@ void poll_yield() {
     if (g_abort.load(std::memory_order_relaxed)) fail("abandoned: another block of the launch failed");
     Fiber* f = b->running;
     f->wait = W_NONE;
+    if ((++b->polls & 63u) == 0) sched_yield();   // other blocks / emulated ranks share the cores
     yield_to_scheduler(b, f);
 }
 
@@ -413,11 +419,54 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     p->multiProcessorCount = simt::env_int("SIMT_SMS", 4);
     return cudaSuccess;
 }
+// Small allocations come from a per-process POSIX shared-memory arena so that cudaIpcGetMemHandle /
+// cudaIpcOpenMemHandle work between emulated ranks (one process per rank, like the real thing).
+namespace simt {
+constexpr size_t kArenaBytes = 8u << 20;
+constexpr size_t kArenaMaxAlloc = 1u << 20;
+static char* g_arena = nullptr;
+static size_t g_arena_used = 0;
+static char g_arena_name[64] = "";
+static std::mutex g_arena_mu;
+struct IpcHandle { unsigned magic; int pid; unsigned long long offset; };
+static std::map<int, char*> g_peer_arenas;
+
+static void arena_unlink() { if (g_arena_name[0]) shm_unlink(g_arena_name); }
+static char* arena_base() {
+    if (g_arena) return g_arena;
+    snprintf(g_arena_name, sizeof(g_arena_name), "/simt_arena_%d", (int)getpid());
+    const int fd = shm_open(g_arena_name, O_CREAT | O_RDWR | O_TRUNC, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)kArenaBytes) != 0) return nullptr;
+    void* p = mmap(nullptr, kArenaBytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return nullptr;
+    atexit(arena_unlink);
+    g_arena = static_cast<char*>(p);
+    return g_arena;
+}
+static bool in_arena(const void* p) {
+    return g_arena && static_cast<const char*>(p) >= g_arena && static_cast<const char*>(p) < g_arena + kArenaBytes;
+}
+}  // namespace simt
+
 cudaError_t cudaMalloc(void** p, size_t bytes) {
+    if (bytes <= simt::kArenaMaxAlloc) {
+        std::lock_guard<std::mutex> lk(simt::g_arena_mu);
+        char* base = simt::arena_base();
+        const size_t need = (bytes + 255) / 256 * 256;
+        if (base && simt::g_arena_used + need <= simt::kArenaBytes) {
+            *p = base + simt::g_arena_used;
+            simt::g_arena_used += need;
+            return cudaSuccess;
+        }
+    }
     *p = aligned_alloc(256, (bytes + 255) / 256 * 256);
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void* p) {
+    if (!simt::in_arena(p)) free(p);   // arena blocks are never reused (test processes are short-lived)
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { memcpy(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) {
     memcpy(dst, src, bytes);
@@ -435,9 +484,33 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+    if (!simt::in_arena(p)) return cudaErrorInvalidValue;
+    simt::IpcHandle ih{0x51a7u, (int)getpid(), (unsigned long long)(static_cast<char*>(p) - simt::g_arena)};
+    memset(h, 0, sizeof(*h));
+    memcpy(h, &ih, sizeof(ih));
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+    simt::IpcHandle ih;
+    memcpy(&ih, &h, sizeof(ih));
+    if (ih.magic != 0x51a7u || ih.offset >= simt::kArenaBytes) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lk(simt::g_arena_mu);
+    char*& base = simt::g_peer_arenas[ih.pid];
+    if (!base) {
+        char name[64];
+        snprintf(name, sizeof(name), "/simt_arena_%d", ih.pid);
+        const int fd = shm_open(name, O_RDWR, 0600);
+        if (fd < 0) return cudaErrorInvalidValue;
+        void* m = mmap(nullptr, simt::kArenaBytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) return cudaErrorInvalidValue;
+        base = static_cast<char*>(m);
+    }
+    *p = base + ih.offset;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 cudaError_t simt_func_set_attribute(size_t bytes) { return bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidValue; }
 cudaError_t simt_occupancy(int* blocks, int threads, size_t smem) {
     *blocks = (threads <= 1024 && smem <= 227 * 1024) ? 1 : 0;

@@ -405,3 +405,27 @@ def test_emulator_reports_deliberate_defects():
             mask = sum(1 << (t % 32) for t in lanes)
             assert np.all(out[lanes].view(np.uint32) == mask), (n, w)
         assert np.all(out[n:] == -1)
+
+
+# ---- multi-rank: one process per emulated rank, peer mailboxes in shared memory ----------------------------------
+@pytest.mark.parametrize('world', [2, 3])
+def test_multi_rank_thinning_and_ksd(world, tmp_path):
+    """The MULTI instantiation of the single-launch kernel (gather by CTA 0 -> peer mailboxes -> re-publish), the
+    mailbox exchange of the launch-per-step kernels, the all-gather fallback and the sharded KSD, on `world`
+    emulated ranks: every rank must return the oracle's index sequence."""
+    import subprocess
+    import sys
+    H.load()                                                  # build once, before the ranks race for it
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'simt_rank_worker.py')
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), str(tmp_path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=600)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and 'SIMT_RANK_OK %d %d' % (r, world) in out, out[-3000:]
