@@ -53,6 +53,11 @@ PROTOTYPES = {
     'gfk_log_weights': (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _dbl, _vp, _pd, _vp, _vp]),
     'gfk_exp_weights': (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _vp]),
     'gfk_gaussian_proxy': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _vp]),
+    'gfk_student_t_proxy': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _dbl, _dbl, _vp, _vp, _vp]),
+    'gfk_kde_ws_bytes': (_sz, [_i64, _i64, _i32]),
+    'gfk_kde_proxy': (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _dbl, _vp, _vp, _vp, _vp]),
+    'gfk_energy_ws_bytes': (_sz, [_i64, _i64]),
+    'gfk_energy_distance_cumulative': (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     'gfk_thin_ws_bytes': (_sz, []),
     'gfk_thin': (ctypes.c_int, [_pp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     'gfk_thin_check': (ctypes.c_int, [_vp, _vp]),

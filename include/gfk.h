@@ -118,6 +118,39 @@ int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f32, void* st
 int gfk_gaussian_proxy(const double* x, int64_t n, int32_t d, const double* mean, const double* prec, double cst,
                        double* log_q, double* grad_q, void* stream);
 
+/* Multivariate Student-t proxy (code/notebooks/lotka_volterra/Gradient_free_Student_t.ipynb#c26-#c31,#c40):
+ * maha = (x - mean)' P (x - mean);  log_q = cst - (df + d)/2 log(1 + maha/df)  with
+ * cst = lgamma((df+d)/2) - lgamma(df/2) - d/2 log(df pi) - 1/2 log det(shape)  (scipy's multivariate_t.logpdf),
+ * grad_q = -(df + d)/df / (1 + maha/df) P (x - mean),  P = shape^-1.  Same layout as gfk_gaussian_proxy.
+ * Asynchronous.  [round 1: executed on the CPU emulator of the test suite only, not yet on a GPU] */
+int gfk_student_t_proxy(const double* x, int64_t n, int32_t d, const double* mean, const double* prec, double df,
+                        double cst, double* log_q, double* grad_q, void* stream);
+
+/* ---- next: (weighted) Gaussian KDE proxy -------------------------------------------------------
+ * Reference: jax/scipy gaussian_kde(sample.T, bw_method='silverman'[, weights=w]).logpdf and its gradient
+ * (code/notebooks/gaussian_mixture/Gaussian_mixture.ipynb#c42-#c54; lotka_volterra/KDE.ipynb#c7-#c11).
+ *   q(p) = sum_j w_j N(p; data_j, H);   log_q[i] = log q(points_i),   grad_q[i] = grad log q(points_i)
+ * data (n, d), points (m, d), weights (n, normalised to sum 1) or NULL for 1/n, all on the device;
+ * whiten (d, d row-major, device): any W with W' W = H^-1 (e.g. the inverse Cholesky factor of H);
+ * log_norm = -0.5 log det(2 pi H).  1 <= d <= 8.  ws: gfk_kde_ws_bytes(n, m, d) bytes of device scratch.
+ * Asynchronous; O(n m) pairs, each d subtractions + 2d FMAs + one exp.
+ * [round 1: executed on the CPU emulator of the test suite only, not yet on a GPU] */
+size_t gfk_kde_ws_bytes(int64_t n, int64_t m, int32_t d);
+int gfk_kde_proxy(const double* data, const double* weights, int64_t n, const double* points, int64_t m, int32_t d,
+                  const double* whiten, double log_norm, double* log_q, double* grad_q, void* ws, void* stream);
+
+/* ---- next: energy distance of every prefix of a thinned sample -----------------------------------
+ * Reference: np.sqrt(dcor.energy_distance(validation, sample[idx[:t]])) for a series of t
+ * (code/notebooks/lotka_volterra/Comparison.ipynb#c19-#c23; definition report/report.tex:437-455).
+ *   e2[t] = 2 mean_{a, u<=t} |x_a - y_u| - mean_{a,b} |x_a - x_b| - mean_{u,v<=t} |y_u - y_v|,  t = 0 .. m-1
+ * (the SQUARED energy distance of x against the first t+1 rows of y; V-statistic means as dcor's default).
+ * x (n, d) validation sample, y (m, d) selected points in selection order, e2 (m), all on the device.  1 <= d <= 8.
+ * ws: gfk_energy_ws_bytes(n, m) bytes of device scratch.  Asynchronous.
+ * [round 1: executed on the CPU emulator of the test suite only, not yet on a GPU] */
+size_t gfk_energy_ws_bytes(int64_t n, int64_t m);
+int gfk_energy_distance_cumulative(const double* x, int64_t n, const double* y, int64_t m, int32_t d, double* e2,
+                                   void* ws, void* stream);
+
 /* ---- a5 + a4: stein_thinning.thinning._greedy_search over the fused integrand -------
  * Greedy selection of m indices (with replacement, first-index tie-break = np.argmin):
  *   A_i = k(i, i);  idx[0] = argmin A;  repeat  A_i += 2 k(i, idx[t-1]);  idx[t] = argmin A.

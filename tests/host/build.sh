@@ -15,7 +15,7 @@ gen="${here}/_gen"
 mkdir -p "${gen}"
 objs=()
 pids=()
-for f in api comm prep thin ksd ${GFK_SIM_EXTRA_UNITS:-}; do
+for f in api comm prep thin ksd proxy energy ${GFK_SIM_EXTRA_UNITS:-}; do
     [ -f "${csrc}/${f}.cu" ] || continue
     python "${here}/simt/cu2cpp.py" "${csrc}/${f}.cu" "${gen}/${f}.cpp"
     g++ -std=c++17 -O2 -g -ffp-contract=off -fPIC -DGFK_SIMT_HOST=1 -Wno-unknown-pragmas -Wno-attributes \
@@ -29,7 +29,7 @@ g++ -std=c++17 -O2 -g -fPIC -DGFK_SIMT_HOST=1 -Wno-unknown-pragmas -I"${here}/si
     -c "${gen}/selftest.cpp" -o "${gen}/selftest.o" &
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
-for f in api comm prep thin ksd ${GFK_SIM_EXTRA_UNITS:-} simt selftest; do [ -f "${gen}/${f}.o" ] && objs+=("${gen}/${f}.o"); done
+for f in api comm prep thin ksd proxy energy ${GFK_SIM_EXTRA_UNITS:-} simt selftest; do [ -f "${gen}/${f}.o" ] && objs+=("${gen}/${f}.o"); done
 g++ -shared -o "${here}/libgfk_sim.so" "${objs[@]}" -ldl -lpthread -lrt
 g++ -std=c++17 -O2 -g -fPIC -shared -o "${here}/libfake_nccl.so" "${here}/simt/fake_nccl.cpp" -lrt -lpthread
 echo "built ${here}/libgfk_sim.so"

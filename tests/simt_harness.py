@@ -232,3 +232,47 @@ class SimProblem:
         out = guarded((ia_d.size,), np.float64, fill=np.nan)
         check(lib.gfk_pairs(ctypes.byref(self.struct), ptr(ia_d), ptr(ib_d), ia_d.size, ptr(out), None))
         return out.copy()
+
+
+# ---- proxies and energy distance through the emulated kernels -----------------------------------
+def student_t_proxy(x, mu, sigma, df):
+    from math import lgamma
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=float)
+    n, d = x.shape
+    cst = lgamma(0.5 * (df + d)) - lgamma(0.5 * df) - d / 2. * np.log(df * np.pi) - 0.5 * np.linalg.slogdet(sigma)[1]
+    xd, md, pd_ = dev(x), dev(mu), dev(np.linalg.inv(sigma))
+    log_q, grad_q = guarded((n,), np.float64, fill=np.nan), guarded((n, d), np.float64, fill=np.nan)
+    check(lib.gfk_student_t_proxy(ptr(xd), n, d, ptr(md), ptr(pd_), ctypes.c_double(df), ctypes.c_double(cst),
+                                  ptr(log_q), ptr(grad_q), None))
+    return log_q.copy(), grad_q.copy()
+
+
+def kde_proxy(sample, weights=None, points=None, bw_method='silverman'):
+    from gradient_free_mcmc_postprocessing_b200.proxies import kde_bandwidth
+    lib = load()
+    sample = np.ascontiguousarray(sample, dtype=float)
+    h, w = kde_bandwidth(sample, weights, bw_method)
+    d = h.shape[0]
+    chol = np.linalg.cholesky(h)
+    whiten = np.ascontiguousarray(np.linalg.inv(chol))
+    log_norm = -0.5 * (d * np.log(2 * np.pi) + 2.0 * np.sum(np.log(np.diag(chol))))
+    data = dev(sample)
+    pts = data if points is None else dev(points)
+    n, m = data.shape[0], pts.shape[0]
+    wd = None if weights is None else dev(w)
+    log_q, grad_q = guarded((m,), np.float64, fill=np.nan), guarded((m, d), np.float64, fill=np.nan)
+    ws = guarded((lib.gfk_kde_ws_bytes(n, m, d),), np.uint8, fill=0xff)
+    check(lib.gfk_kde_proxy(ptr(data), ptr(wd), n, ptr(pts), m, d, ptr(dev(whiten)), ctypes.c_double(log_norm),
+                            ptr(log_q), ptr(grad_q), ptr(ws), None))
+    return log_q.copy(), grad_q.copy()
+
+
+def energy_cumulative(x, y):
+    lib = load()
+    xd, yd = dev(x), dev(y)
+    n, m, d = xd.shape[0], yd.shape[0], xd.shape[1]
+    e2 = guarded((m,), np.float64, fill=np.nan)
+    ws = guarded((lib.gfk_energy_ws_bytes(n, m),), np.uint8, fill=0xff)
+    check(lib.gfk_energy_distance_cumulative(ptr(xd), n, ptr(yd), m, d, ptr(e2), ptr(ws), None))
+    return e2.copy()

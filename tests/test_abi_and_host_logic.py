@@ -176,3 +176,29 @@ def test_pick_winner_matches_device_comparator_semantics():
     assert pick_winner([np.nan, np.nan], [8, 3]) == 3
     assert pick_winner([np.inf, np.inf], [2, 1]) == 1
     assert pick_winner([-np.inf, 0.0], [7, 0]) == 7
+
+
+def test_next_row_host_logic(tmp_path):
+    """kde_bandwidth = scipy's gaussian_kde covariance and weights; the chain layer's dealing and .npy round trip."""
+    from scipy.stats import gaussian_kde
+    from gradient_free_mcmc_postprocessing_b200 import chains, proxies
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((300, 3))
+    w = rng.random(300)
+    for weights in (None, w):
+        for bw in ('silverman', 'scott', 0.3):
+            kde = gaussian_kde(x.T, bw_method=bw, weights=weights)
+            h, wn = proxies.kde_bandwidth(x, weights, bw)
+            np.testing.assert_allclose(h, kde.covariance, rtol=1e-13)
+            np.testing.assert_allclose(wn, kde.weights, rtol=1e-15)
+    with pytest.raises(ValueError):
+        proxies.kde_bandwidth(x, w[:-1])
+    with pytest.raises(ValueError):
+        proxies.kde_bandwidth(x, None, 'nonsense')
+    assert chains._my_chains(5, 0, 2) == [0, 2, 4] and chains._my_chains(5, 1, 2) == [1, 3]
+    p = chains.save_indices(tmp_path / 'idx.npy', np.array([3, 1, 2]))
+    got = chains.load_array(p)
+    assert got.dtype == np.uint32 and np.array_equal(got, [3, 1, 2])
+    assert chains.load_array(x) is x
+    with pytest.raises(ValueError):
+        chains.thin_chains([x], [x, x], 3)

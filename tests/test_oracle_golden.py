@@ -112,3 +112,34 @@ def test_preconditioners(g13):
         linv = ok.make_precon(s, pre)
         assert linv.shape == (d, d) and np.all(np.linalg.eigvals(linv) > 0)
     assert np.allclose(ok.make_precon(s, '2.5'), np.identity(2) / 2.5)
+
+
+# ---- the oracle of the steps either side of the path ----------------------------------------------
+def test_kde_proxy_golden_unique_counts(g45):
+    """Gaussian_mixture.ipynb#c42-#c54,#c67: thin_gf with the KDE / weighted-KDE proxy selects 481 / 343 unique
+    points of the seeded mixture sample - pins oracle.next_rows.kde_logpdf_and_score."""
+    from oracle import next_rows as nr
+    x, log_p = g45['sample'], g45['log_p']
+    log_q, gradient_q = nr.kde_logpdf_and_score(x)
+    idx = ot.thin_gf(x, log_p, log_q, gradient_q, 1000, preconditioner='med')
+    assert len(np.unique(idx)) == 481
+    p = np.exp(log_p)
+    log_q, gradient_q = nr.kde_logpdf_and_score(x, weights=p / np.sum(p))
+    idx = ot.thin_gf(x, log_p, log_q, gradient_q, 1000, preconditioner='med')
+    assert len(np.unique(idx)) == 343
+
+
+def test_student_t_oracle_matches_scipy_like_the_notebook():
+    """Gradient_free_Student_t.ipynb#c30: np.testing.assert_allclose(t_log_pdf(...), multivariate_t.logpdf(...))."""
+    from scipy import stats
+    from oracle import next_rows as nr
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((500, 4)) * 0.02 + np.array([-0.38, 0.29, -0.02, -0.018])
+    a = rng.standard_normal((4, 4))
+    scale = 1e-4 * (a @ a.T / 4 + 0.5 * np.eye(4))
+    mu = x.mean(0)
+    np.testing.assert_allclose(nr.t_log_pdf(x, mu, scale, 9.0), stats.multivariate_t.logpdf(x, loc=mu, shape=scale, df=9.0))
+    eps = 1e-7
+    num = np.array([(nr.t_log_pdf(x + eps * np.eye(4)[k], mu, scale, 9.0) - nr.t_log_pdf(x - eps * np.eye(4)[k], mu, scale, 9.0))
+                    / (2 * eps) for k in range(4)]).T
+    np.testing.assert_allclose(nr.t_grad_log_pdf(x, mu, scale, 9.0), num, rtol=1e-5, atol=1e-3)

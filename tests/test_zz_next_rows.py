@@ -1,7 +1,8 @@
-"""SURVEY.md section 8f ("next") rows.  These GPU tests were written in round 1 after GPU access had been closed
-for the round, so the code under them has only been checked on the host (formula order against scipy / einsum).
-They are non-strict xfail until a GPU run has confirmed them: a pass shows up as XPASS, a failure does not mask
-the verified suite.  The file sorts last on purpose (the driver runs pytest with -x).
+"""SURVEY.md section 8f ("next") rows on the GPU.  These tests were written in round 1 after GPU access had been
+closed for the round: the kernels under them have been executed by the CPU emulator of the test suite
+(tests/test_simt_kernels.py, tests/test_simt_next_rows.py - same cases) but not yet on a B200.  They are non-strict
+xfail until a GPU run has confirmed them: a pass shows up as XPASS, a failure does not mask the verified suite.  The
+file sorts last on purpose (the driver runs pytest with -x).
 """
 import warnings
 
@@ -42,3 +43,75 @@ def test_gaussian_thin_with_device_proxy_matches_reference_glue(gpu_device, g45)
         idx = gaussian_thin(g45['sample'], g45['log_p'], g45['laplace_mean'], g45['laplace_cov'], 30,
                             proxy_on_device=True, device=gpu_device)
     assert np.array_equal(idx, g45['glue_gaussian_thin_laplace_30'])
+
+
+def test_student_t_proxy_on_device(gpu_device):
+    from scipy import stats
+    from gradient_free_mcmc_postprocessing_b200 import proxies
+    from oracle import next_rows as nr
+    rng = np.random.default_rng(44)
+    d = 4
+    x = rng.standard_normal((20_000, d)) * 2 + 1
+    a = rng.standard_normal((d, d))
+    sigma = a @ a.T / d + 0.5 * np.eye(d)
+    mu = rng.standard_normal(d)
+    np.testing.assert_allclose(proxies.t_log_pdf(x, mu, sigma, 9.0, device=gpu_device),
+                               stats.multivariate_t.logpdf(x, loc=mu, shape=sigma, df=9.0), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(proxies.t_grad_log_pdf(x, mu, sigma, 9.0, device=gpu_device),
+                               nr.t_grad_log_pdf(x, mu, sigma, 9.0), rtol=1e-12, atol=1e-13)
+    log_p = -0.5 * np.sum(x ** 2, axis=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        got = proxies.thin_gf_t(x, log_p, mu, sigma, 9.0, 30, device=gpu_device)
+        assert np.array_equal(got, nr.thin_gf_t(x, log_p, mu, sigma, 9.0, 30))
+
+
+def test_kde_proxy_on_device_golden_counts(gpu_device, g45):
+    """Gaussian_mixture.ipynb#c67: 481 unique points with the KDE proxy, 343 with the weighted KDE proxy."""
+    from scipy.stats import gaussian_kde
+    from gradient_free_mcmc_postprocessing_b200 import proxies
+    from oracle import next_rows as nr
+    x, log_p = g45['sample'], g45['log_p']
+    log_q, grad_q = proxies.kde_logpdf_and_score(x, device=gpu_device)
+    np.testing.assert_allclose(log_q, gaussian_kde(x.T, bw_method='silverman').logpdf(x.T), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(grad_q, nr.kde_logpdf_and_score(x)[1], rtol=2e-8, atol=1e-10)
+    assert len(np.unique(proxies.kde_thin(x, log_p, 1000, device=gpu_device))) == 481
+    w = np.exp(log_p) / np.sum(np.exp(log_p))
+    assert len(np.unique(proxies.kde_thin(x, log_p, 1000, weights=w, device=gpu_device))) == 343
+    rng = np.random.default_rng(5)
+    data, pts = rng.standard_normal((30_000, 4)), rng.standard_normal((2_000, 4)) * 2
+    log_q, grad_q = proxies.kde_logpdf_and_score(data, points=pts, device=gpu_device)
+    want_lq, want_g = nr.kde_logpdf_and_score(data, points=pts)
+    np.testing.assert_allclose(log_q, want_lq, rtol=1e-12, atol=1e-11)
+    np.testing.assert_allclose(grad_q, want_g, rtol=2e-8, atol=1e-10)
+
+
+def test_cumulative_energy_distance_on_device(gpu_device):
+    from gradient_free_mcmc_postprocessing_b200 import proxies
+    from oracle import next_rows as nr
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((5_000, 4))
+    y = rng.standard_normal((1_000, 4)) * 1.2 + 0.1
+    e2 = proxies.cumulative_energy_distance(x, y, device=gpu_device)
+    for t in (0, 1, 17, 499, 999):
+        want = nr.energy_distance(x, y[:t + 1])
+        assert abs(e2[t] - want) <= 1e-12 * max(1.0, abs(want)), (t, e2[t], want)
+    assert abs(proxies.fit_quality(x, y, 10, device=gpu_device) - nr.fit_quality(x, y, 10)) < 1e-12
+
+
+def test_chain_batched_thinning_and_npy_layer(gpu_device, g13, tmp_path):
+    from gradient_free_mcmc_postprocessing_b200.chains import thin_chains
+    paths = []
+    for i in range(3):
+        sp, gp = tmp_path / f'rw_samples_{i}.npy', tmp_path / f'rw_grads_{i}.npy'
+        np.save(sp, g13['sample'][i * 100:])
+        np.save(gp, g13['gradient'][i * 100:])
+        paths.append((sp, gp))
+    outs = [tmp_path / f'rw_thinned_idx_{i}.npy' for i in range(3)]
+    res = thin_chains([p[0] for p in paths], [p[1] for p in paths], 20, out_paths=outs, device=gpu_device)
+    assert np.array_equal(res[0], g13['idx_thin'])
+    from oracle.stein_thinning_oracle.thinning import thin as oracle_thin
+    for i in range(3):
+        assert np.array_equal(np.load(outs[i]), oracle_thin(g13['sample'][i * 100:], g13['gradient'][i * 100:], 20))
+    mine = thin_chains([p[0] for p in paths], [p[1] for p in paths], 20, rank=1, world=2, device=gpu_device)
+    assert mine[0] is None and mine[2] is None and np.array_equal(mine[1], res[1])
