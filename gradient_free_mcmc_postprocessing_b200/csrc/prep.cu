@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) lw_minmax_kernel(const double* __restrict
     __shared__ double sh_min[8], sh_max[8], sh_bad[8];
     double mn = INFINITY, mx = -INFINITY, bad = 0.0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const double a = log_p[e], b = log_q[e];
+        const double a = log_p ? log_p[e] : 0.0, b = log_q[e];     // log_p == nullptr: statistics of log_q itself
         if (isnan(a) || isnan(b)) bad += 1.0;
         const double v = __dsub_rn(b, a);
         mn = fmin(mn, v);
@@ -431,6 +431,28 @@ extern "C" int gfk_log_weights(const double* log_p, const double* log_q, int64_t
     lw_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(log_p, log_q, n, use_cap, mx, range_cap, lw);
     count_launches(2);
     GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" int gfk_log_weights_range(const double* lw, int64_t n, double* min_max_host, void* ws, void* stream) {
+    GFK_REQUIRE(lw && min_max_host && ws && n >= 1, "gfk_log_weights_range: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int grid = grid_for(n, 256);
+    if (grid > 1024) grid = 1024;
+    double* stats = static_cast<double*>(ws);
+    lw_minmax_kernel<<<grid, 256, 0, st>>>(nullptr, lw, n, stats);
+    count_launches(1);
+    GFK_CHECK_LAUNCH();
+    std::vector<double> h(3 * (size_t)grid);
+    GFK_CUDA(cudaMemcpyAsync(h.data(), stats, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    GFK_CUDA(cudaStreamSynchronize(st));
+    double mn = INFINITY, mx = -INFINITY;
+    for (int b = 0; b < grid; ++b) {
+        mn = fmin(mn, h[3 * b]);
+        mx = fmax(mx, h[3 * b + 1]);
+    }
+    min_max_host[0] = mn;
+    min_max_host[1] = mx;
     return GFK_OK;
 }
 

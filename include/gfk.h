@@ -110,6 +110,10 @@ size_t gfk_log_weights_ws_bytes(void);
 int gfk_log_weights(const double* log_p, const double* log_q, int64_t n, int use_cap, double range_cap,
                     double* lw, double* spread_host, void* ws, void* stream);
 int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f32, void* stream);
+/* min and max of a log-weight vector (host out, 2 doubles).  SYNCHRONOUS.  The KSD row sums may use the
+ * pre-exponentiated weights w = exp(lw) (one multiplication per pair instead of one exp) whenever every |lw| is far
+ * from the overflow / underflow range of exp; the caller decides with this.  ws: gfk_log_weights_ws_bytes(). */
+int gfk_log_weights_range(const double* lw, int64_t n, double* min_max_host, void* ws, void* stream);
 
 /* ---- next: the Gaussian proxy of gaussian_thin, code/src/thinning.py:15-16 ----------------
  * log_q[i] = -0.5 (cst + (x_i - mean)' P (x_i - mean)) with cst = d log(2 pi) + log det(cov) (what scipy's

@@ -429,3 +429,32 @@ def test_multi_rank_thinning_and_ksd(world, tmp_path):
                 p.kill()
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and 'SIMT_RANK_OK %d %d' % (r, world) in out, out[-3000:]
+
+
+def test_ksd_weights_preexponentiated_only_when_safe():
+    """Strict-mode KSD multiplies by w_i w_j = exp(lw_i) exp(lw_j) (gfk_log_weights_range says when that is safe) and
+    falls back to exp(lw_i + lw_j) per pair when a log-weight is extreme - both within 1e-10 of the oracle."""
+    rng = np.random.default_rng(81)
+    n = 200
+    x, g = _mcmc_like(rng, n, 3, dup=0.0)
+    log_p = -0.5 * np.sum(x ** 2, axis=1)
+    for shift, safe in ((0.0, True), (650.0, False)):
+        log_q = log_p + np.sin(x[:, 0])
+        log_q[::2] += shift            # lw_i = +650 and lw_j = -650 pairs: exp(lw_i) overflows, exp(lw_i + lw_j) does not
+        log_q[1::2] -= shift
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med')
+        p = H.SimProblem(x, g, log_p, log_q, preconditioner='med')
+        low, diag = p.ksd_rowsums()
+        assert np.allclose(p.lw_range, (np.min(log_q - log_p), np.max(log_q - log_p)), rtol=0, atol=0)
+        assert (p._struct_ksd.w is not None) == safe
+        with np.errstate(over='ignore', invalid='ignore'):
+            km = os_.kmat(ref, n)
+        if safe:
+            np.testing.assert_allclose(p.ksd(), os_.ksd(ref, n), rtol=1e-10)
+        else:
+            # row sums mix magnitudes e^+-1300; compare the finite, well-scaled entries pair by pair instead
+            ia, ib = np.arange(0, n, 2), np.arange(1, n, 2)
+            np.testing.assert_allclose(p.pairs(ia, ib), km[ia, ib], rtol=1e-10)
+            assert np.all(np.isfinite(low[1::2]) | np.isinf(low[1::2]))
