@@ -458,3 +458,50 @@ def test_ksd_weights_preexponentiated_only_when_safe():
             ia, ib = np.arange(0, n, 2), np.arange(1, n, 2)
             np.testing.assert_allclose(p.pairs(ia, ib), km[ia, ib], rtol=1e-10)
             assert np.all(np.isfinite(low[1::2]) | np.isinf(low[1::2]))
+
+
+# ---- edge sizes and BASELINE-shaped inputs -----------------------------------------------------------------------
+@pytest.mark.parametrize('n', [1, 2, 3, 31, 32, 33, 511, 512, 513, 1025])
+def test_edge_sizes_all_strategies(n, monkeypatch):
+    """Fewer rows than threads, exactly one CTA, one row more than a CTA, a single row; m = 1; every d path."""
+    rng = np.random.default_rng(900 + n)
+    for d in (1, 2, 3, 4, 5, 9):
+        x = rng.standard_normal((n, d))
+        g = -x * (1 + 0.1 * np.arange(d))
+        if n > 3:
+            x[n // 2], g[n // 2] = x[1], g[1]                     # an exact duplicate
+        for m in (1, 2, 7):
+            expect = ot.thin(x, g, m, standardize=(n > 1))
+            for env in STRATEGIES.values():
+                for k in ('GFK_PERSISTENT', 'GFK_RESIDENT'):
+                    monkeypatch.delenv(k, raising=False)
+                for k, v in env.items():
+                    monkeypatch.setenv(k, v)
+                idx, obj = H.SimProblem(x, g, standardize=(n > 1)).thin(m)
+                assert np.array_equal(idx, expect), (n, d, m, env)
+                assert np.all(np.isfinite(obj))
+        if n >= 2:
+            p = H.SimProblem(x, g, standardize=(n > 1), preconditioner='id', precision='f64-fast')
+            ref = ot._make_stein_integrand(x, g, standardize=(n > 1))
+            np.testing.assert_allclose(p.ksd(), os_.ksd(ref, n), rtol=1e-10)
+
+
+def test_config_c1_full_size_and_c2_prefix_through_the_emulator():
+    """BASELINE config C1 in full (n = 10^4, d = 2, m = 100, gradient-free, 'med') and a prefix of the C2-shaped
+    chain (d = 4, runs of exactly duplicated rows, score magnitudes 1e2-1e3) at 60 000 rows on 5 emulated SMs."""
+    from gradient_free_mcmc_postprocessing_b200 import synthetic
+    os.environ['SIMT_SMS'] = '5'
+    try:
+        c = synthetic.config_c1()
+        expect = ot.thin_gf(c['sample'], c['log_p'], c['log_q'], c['gradient_q'], c['m'], preconditioner='med')
+        idx, _ = H.SimProblem(c['sample'], c['gradient_q'], c['log_p'], c['log_q'], preconditioner='med').thin(c['m'])
+        assert np.array_equal(idx, expect)
+        c = synthetic.config_c2(n=60_000, m=30)
+        expect = ot.thin(c['sample'], c['gradient'], 30, preconditioner='med')
+        for precision in ('f64', 'f64-fast'):
+            idx, _ = H.SimProblem(c['sample'], c['gradient'], preconditioner='med', precision=precision).thin(30)
+            assert np.array_equal(idx, expect), precision
+        first_of_run = np.concatenate([[True], np.any(c['sample'][1:] != c['sample'][:-1], axis=1)])
+        assert np.all(first_of_run[idx])
+    finally:
+        os.environ.pop('SIMT_SMS', None)
