@@ -1,0 +1,65 @@
+"""Timings of everything that has not been measured on a GPU yet (round 1 ended with GPU access closed):
+full-size C4 KSD, the strict-mode KSD with pre-exponentiated weights, the section-8f kernels (proxies, KDE, energy
+distance).  Writes gpurun_out/next_rows_probe.json.  Development tool; run under gpurun on one B200."""
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gradient_free_mcmc_postprocessing_b200 import proxies, synthetic  # noqa: E402
+from gradient_free_mcmc_postprocessing_b200._engine import SteinProblem  # noqa: E402
+
+warnings.simplefilter('ignore')
+out = {}
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def note(key, **kw):
+    out[key] = kw
+    print(key, kw, flush=True)
+
+
+# C4: full O(n^2) gradient-free KSD, d = 10, 'med' (BASELINE.json configs[3])
+for n in (50_000, 200_000):
+    c = synthetic.config_c4(n=n)
+    for prec in ('f64', 'f64-fast', 'f32'):
+        p = SteinProblem(c['sample'], c['gradient_q'], log_p=c['log_p'], log_q=c['log_q'], preconditioner='med',
+                         precision=prec)
+        t = timed(lambda: p.ksd(None, n), reps=2)
+        pairs = n * (n + 1) / 2
+        note(f'ksd_c4:{n}:{prec}', seconds=t, pair_evals_per_s=pairs / t, fp64_tflops_algorithmic=pairs * 99 / t / 1e12)
+    del p
+
+# section 8f kernels
+rng = np.random.default_rng(0)
+for n, d in ((100_000, 4), (200_000, 2)):
+    x = torch.from_numpy(rng.standard_normal((n, d))).cuda()
+    t = timed(lambda: proxies.kde_logpdf_and_score(x, return_device=True), reps=2)
+    note(f'kde:{n}:{d}', seconds=t, pairs_per_s=n * n / t)
+xv = torch.from_numpy(rng.standard_normal((50_000, 4))).cuda()
+yv = torch.from_numpy(rng.standard_normal((10_000, 4))).cuda()
+t = timed(lambda: proxies.cumulative_energy_distance(xv, yv), reps=2)
+note('energy:50000x10000:4', seconds=t, pairs_per_s=(50_000 ** 2 / 2 + 50_000 * 10_000 + 10_000 ** 2 / 2) / t)
+x = torch.from_numpy(rng.standard_normal((1_000_000, 4))).cuda()
+cov = np.eye(4) + 0.1
+t = timed(lambda: proxies._t_proxy_device(x, np.zeros(4), cov, 9.0))
+note('student_t:1e6:4', seconds=t, gb_per_s=1_000_000 * (32 + 8 + 32) / t / 1e9)
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'next_rows_probe.json'), 'w'), indent=1)
