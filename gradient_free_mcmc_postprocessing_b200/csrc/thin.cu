@@ -14,6 +14,8 @@
 #include <stddef.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "comm.h"
 
@@ -912,6 +914,9 @@ static cudaError_t persistent_prepare(K kernel, int threads, size_t smem) {
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_cooperative(void (*kernel)(KArgs...), unsigned grid, int threads, size_t smem, cudaStream_t st,
                                       Args... args) {
+    // cudaLaunchCooperativeKernel reads each argument through an untyped pointer: the types must be the kernel's own
+    static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count differs from the kernel's parameter list");
+    static_assert((std::is_same<KArgs, Args>::value && ...), "argument types differ from the kernel's parameter list");
 #if defined(GFK_SIMT_HOST)
     (void)st;
     simt::launch(dim3(grid), dim3((unsigned)threads), smem, true, [=]() { kernel(args...); });
