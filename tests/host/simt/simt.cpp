@@ -48,7 +48,13 @@ simt_switch:
 namespace simt {
 
 constexpr size_t kStackBytes = 64 * 1024;
-enum Wait { W_NONE = 0, W_BLOCK = 1, W_WARP = 2 };
+enum Wait { W_NONE = 0, W_BLOCK = 1, W_WARP = 2, W_NAMED = 3 };
+
+struct NamedBarrier {
+    unsigned gen = 0;
+    int arrived = 0;
+    int count = 0;
+};
 
 struct WarpState {
     unsigned long long buf[2][32];
@@ -67,11 +73,13 @@ struct Fiber {
     bool done = false;
     int warp = 0, lane = 0;
     unsigned last_mask = 0;
+    int wait_id = 0;
 };
 
 struct Block {
     std::vector<Fiber> fibers;
     std::vector<WarpState> warps;
+    NamedBarrier named[16];
     unsigned gen = 0;
     int arrived = 0;
     int alive = 0;
@@ -166,6 +174,31 @@ void syncthreads(const char* file, int line) {
     yield_to_scheduler(b, f);
 }
 
+void named_barrier(int id, int count, bool wait) {
+    Block* b = t_blk;
+    Fiber* f = b->running;
+    if (id < 1 || id > 15 || count <= 0 || count % 32 != 0) fail("named barrier %d with thread count %d", id, count);
+    NamedBarrier& nb = b->named[id];
+    if (nb.arrived == 0) nb.count = count;
+    else if (nb.count != count) fail("named barrier %d used with thread counts %d and %d", id, nb.count, count);
+    const unsigned g = nb.gen;
+    if (++nb.arrived == nb.count) {
+        nb.arrived = 0;
+        nb.gen++;
+        if (random_sched()) { f->wait = W_NONE; yield_to_scheduler(b, f); }
+        return;
+    }
+    if (nb.arrived > nb.count) fail("named barrier %d: more arrivals than its thread count %d", id, count);
+    if (!wait) {
+        if (random_sched()) { f->wait = W_NONE; yield_to_scheduler(b, f); }
+        return;
+    }
+    f->wait = W_NAMED;
+    f->wait_id = id;
+    f->wait_gen = g;
+    yield_to_scheduler(b, f);
+}
+
 const unsigned long long* warp_gather(unsigned long long bits) {
     Block* b = t_blk;
     Fiber* f = b->running;
@@ -244,6 +277,7 @@ static inline bool runnable(const Block& b, const Fiber& f) {
     if (f.done) return false;
     if (f.wait == W_NONE) return true;
     if (f.wait == W_BLOCK) return b.gen != f.wait_gen;
+    if (f.wait == W_NAMED) return b.named[f.wait_id].gen != f.wait_gen;
     return b.warps[f.warp].gen != f.wait_gen;
 }
 
@@ -255,6 +289,7 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
     b.alive = T;
     b.failed = false;
     b.warps.assign((size_t)nwarps, WarpState());
+    for (NamedBarrier& nb : b.named) nb = NamedBarrier();
     if (smem_bytes) memset(b.smem, 0xff, smem_bytes);   // poison: NaN patterns / huge integers
     uint3 bid;
     bid.x = linear_block % grid.x;
@@ -302,15 +337,15 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
             }
         }
         if (pick < 0) {
-            int at_block = 0, at_warp = 0;
+            int at_block = 0, at_warp = 0, at_named = 0;
             for (const Fiber& f : b.fibers) {
                 if (f.done) continue;
-                if (f.wait == W_BLOCK) ++at_block; else if (f.wait == W_WARP) ++at_warp;
+                if (f.wait == W_BLOCK) ++at_block; else if (f.wait == W_WARP) ++at_warp; else if (f.wait == W_NAMED) ++at_named;
             }
             char msg[256];
             snprintf(msg, sizeof(msg),
-                     "deadlock in block %u: %d threads alive, %d wait in __syncthreads, %d in a warp collective "
-                     "(divergent barrier?)", linear_block, b.alive, at_block, at_warp);
+                     "deadlock in block %u: %d threads alive, %d wait in __syncthreads, %d in a warp collective, "
+                     "%d at a named barrier (divergent barrier?)", linear_block, b.alive, at_block, at_warp, at_named);
             record_error(msg);
             g_abort.store(true);
             b.failed = true;
@@ -322,6 +357,16 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
         b.running = &f;
         simt_switch(&b.sched_sp, f.sp);
         b.running = nullptr;
+    }
+    if (!b.failed) {
+        for (int id = 1; id < 16; ++id) {
+            if (b.named[id].arrived != 0) {
+                char msg[160];
+                snprintf(msg, sizeof(msg), "block %u exited with %d of %d arrivals pending at named barrier %d",
+                         linear_block, b.named[id].arrived, b.named[id].count, id);
+                record_error(msg);
+            }
+        }
     }
 }
 

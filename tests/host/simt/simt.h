@@ -54,6 +54,8 @@ struct ThreadCtx {
 ThreadCtx* cur();                       // the running fiber
 void* dyn_smem();                       // this block's dynamic shared memory
 void syncthreads(const char* file, int line);
+// PTX bar.sync / bar.arrive on named barrier `id` (1..15) expecting `count` threads; wait: bar.sync
+void named_barrier(int id, int count, bool wait);
 // every lane of the warp contributes 64 bits; returns the 32 contributions (valid until the next collective)
 const unsigned long long* warp_gather(unsigned long long bits);
 unsigned warp_alive_mask();

@@ -505,3 +505,31 @@ def test_config_c1_full_size_and_c2_prefix_through_the_emulator():
         assert np.all(first_of_run[idx])
     finally:
         os.environ.pop('SIMT_SMS', None)
+
+
+@pytest.mark.parametrize('d', [1, 4, 10, 32])
+def test_warp_specialised_ksd_kernel_equals_the_tile_kernel(d, monkeypatch):
+    """GFK_KSD_WS=1: producer warp + named-barrier ring (ksd_rowsum_ws_kernel) must give bit-identical row sums to
+    ksd_rowsum_kernel - same pair arithmetic, same summation order - for any thread schedule."""
+    rng = np.random.default_rng(8000 + d)
+    n = 330                                                # 6 row tiles: the ring of 3 buffers wraps
+    x, g = _mcmc_like(rng, n, d, dup=0.1)
+    log_p = -0.5 * np.sum(x ** 2, axis=1)
+    log_q = log_p + np.sin(x[:, 0])
+    sel = rng.integers(0, n, 200)
+    for prec in ('f64', 'f32'):
+        for gf in (False, True):
+            mk = (lambda: H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=prec)) if gf else \
+                 (lambda: H.SimProblem(x, g, preconditioner='med', precision=prec))
+            monkeypatch.delenv('GFK_KSD_WS', raising=False)
+            p = mk()
+            base, base_sel = p.ksd_rowsums(), p.ksd_rowsums(sel=sel, part=1, n_parts=2)
+            monkeypatch.setenv('GFK_KSD_WS', '1')
+            for random, seed in ((False, 0), (True, 1), (True, 2)):
+                H.set_schedule(random, seed)
+                got, got_sel = p.ksd_rowsums(), p.ksd_rowsums(sel=sel, part=1, n_parts=2)
+                assert np.array_equal(got[0], base[0]) and np.array_equal(got[1], base[1]), (prec, gf, random, seed)
+                assert np.array_equal(got_sel[0], base_sel[0]), (prec, gf, random, seed)
+            H.set_schedule(False)
+    ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med')
+    np.testing.assert_allclose(H.SimProblem(x, g, log_p, log_q, preconditioner='med').ksd(), os_.ksd(ref, n), rtol=1e-10)

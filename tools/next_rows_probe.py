@@ -42,9 +42,14 @@ for n in (50_000, 200_000):
     for prec in ('f64', 'f64-fast', 'f32'):
         p = SteinProblem(c['sample'], c['gradient_q'], log_p=c['log_p'], log_q=c['log_q'], preconditioner='med',
                          precision=prec)
-        t = timed(lambda: p.ksd(None, n), reps=2)
         pairs = n * (n + 1) / 2
-        note(f'ksd_c4:{n}:{prec}', seconds=t, pair_evals_per_s=pairs / t, fp64_tflops_algorithmic=pairs * 99 / t / 1e12)
+        for ws in ('0', '1'):                        # 1: warp-specialised producer / consumer kernel (opt-in)
+            os.environ['GFK_KSD_WS'] = ws
+            ks = p.ksd(None, min(n, 20_000))
+            t = timed(lambda: p.ksd(None, n), reps=2)
+            note(f'ksd_c4:{n}:{prec}:ws{ws}', seconds=t, pair_evals_per_s=pairs / t,
+                 fp64_tflops_algorithmic=pairs * 99 / t / 1e12, ks_last=float(ks[-1]))
+        os.environ.pop('GFK_KSD_WS', None)
     del p
 
 # section 8f kernels
