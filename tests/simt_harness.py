@@ -72,21 +72,19 @@ def check(rc):
         raise SimError('libgfk (emulated) error %d: %s' % (rc, load().gfk_last_error().decode('utf-8', 'replace')))
 
 
-_keep = []   # the mappings must outlive the arrays that view them
-
-
 def guarded(shape, dtype, fill=None):
     """ndarray whose last byte sits (up to alignment) right before a PROT_NONE page."""
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
     span = (max(nbytes, 1) + _PAGE - 1) // _PAGE * _PAGE
-    mm = mmap.mmap(-1, span + _PAGE)
-    base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+    mm = mmap.mmap(-1, span + _PAGE)                 # stays mapped as long as the returned array (its .base) lives
+    probe = ctypes.c_char.from_buffer(mm)
+    base = ctypes.addressof(probe)
+    del probe
     if _libc.mprotect(ctypes.c_void_p(base + span), ctypes.c_size_t(_PAGE), 0) != 0:
         raise OSError(ctypes.get_errno(), 'mprotect')
     off = (span - nbytes) // 16 * 16
     arr = np.frombuffer(mm, dtype=dtype, count=int(np.prod(shape, dtype=np.int64)), offset=off).reshape(shape)
-    _keep.append(mm)
     if fill is not None:
         arr[...] = fill
     return arr
