@@ -280,7 +280,8 @@ def kde_proxy(sample, weights=None, points=None, bw_method='silverman'):
     wd = None if weights is None else dev(w)
     log_q, grad_q = guarded((m,), np.float64, fill=np.nan), guarded((m, d), np.float64, fill=np.nan)
     ws = guarded((lib.gfk_kde_ws_bytes(n, m, d),), np.uint8, fill=0xff)
-    check(lib.gfk_kde_proxy(ptr(data), ptr(wd), n, ptr(pts), m, d, ptr(dev(whiten)), ctypes.c_double(log_norm),
+    whiten_d = dev(whiten)                            # a named reference: the mapping lives as long as the array
+    check(lib.gfk_kde_proxy(ptr(data), ptr(wd), n, ptr(pts), m, d, ptr(whiten_d), ctypes.c_double(log_norm),
                             ptr(log_q), ptr(grad_q), ptr(ws), None))
     return log_q.copy(), grad_q.copy()
 
