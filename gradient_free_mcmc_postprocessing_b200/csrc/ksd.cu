@@ -49,12 +49,12 @@ __device__ __forceinline__ long long row_of(const KsdArgs<T>& a, long long t) {
 }
 
 // ---- asynchronous global -> shared copies (LDGSTS): no register staging, overlap with the FMA loop ----
-#if defined(GFK_SIMT_HOST)   // CPU emulation build of the test suite: synchronous copies
-__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) { *dst = *src; }
-__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) { *dst = *src; }
-__device__ __forceinline__ void cp_async_commit() {}
+#if defined(GFK_SIMT_HOST)   // CPU emulation build of the test suite: the emulator defers the copies like the hardware
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) { simt::cp_async(dst, src, 8); }
+__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) { simt::cp_async(dst, src, 4); }
+__device__ __forceinline__ void cp_async_commit() { simt::cp_async_commit(); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() {}
+__device__ __forceinline__ void cp_async_wait() { simt::cp_async_wait(N); }
 #else
 __device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);

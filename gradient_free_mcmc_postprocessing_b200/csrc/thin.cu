@@ -622,6 +622,219 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
     grid_argmin_publish(bv, bi, a);
 }
 
+// ---- the same step with a software pipeline: NST slabs in flight per CTA (cp.async), one CTA per SM ----------
+// thin_step_chunked_kernel loads a slab, waits for it, consumes it, and relies on the three CTAs of an SM to overlap
+// one another.  Here ONE CTA per SM keeps NST - 1 slabs (64 KB each in float64) in flight with cp.async while it
+// consumes the oldest, so the HBM request stream never drains.  Per-row arithmetic and summation order are those of
+// thin_step_chunked_kernel (bit-identical results); the row state lives in ChunkRow so the slab loop can be
+// flattened over (tile, slab) stages.
+// [round 1: opt-in with GFK_CHUNK_PIPE=1; executed on the CPU emulator of the test suite only, not yet on a GPU]
+#if defined(GFK_SIMT_HOST)
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) { simt::cp_async(dst, src, 8); }
+__device__ __forceinline__ void cp_async8(float* dst, const float* src) { simt::cp_async(dst, src, 4); }
+__device__ __forceinline__ void cp_async_commit_group() { simt::cp_async_commit(); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { simt::cp_async_wait(N); }
+#else
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
+}
+__device__ __forceinline__ void cp_async8(float* dst, const float* src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
+
+// running sums of one row across the slabs, numpy's order (see thin_step_chunked_kernel)
+template <typename T, bool STRICT, bool DENSE>
+struct ChunkRow {
+    double s1, s2, s3, s4, r0, r1, r2, r3, r4, r5, r6, r7;   // strict
+    T rr, uu, su, ss;                                         // fast
+
+    __device__ __forceinline__ void reset() {
+        s1 = s2 = s3 = s4 = 0.0;
+        r0 = r1 = r2 = r3 = r4 = r5 = r6 = r7 = 0.0;
+        rr = uu = su = ss = T(0);
+    }
+
+    __device__ __forceinline__ void slab(const T* xr, const T* sr, const T* xlr, const T* ysh, const T* sysh,
+                                         const T* ylsh, int k0, int kc, int d, int d8, const KParams& kp) {
+        if constexpr (STRICT) {
+            for (int k = 0; k < kc; ++k) {
+                const double r = nf_sub(xr[k], ysh[k0 + k]);
+                const double pa = nf_mul(nf_mul(kp.lambda, r), r);
+                const double pb = nf_mul(nf_mul(kp.lambda_sq, r), r);
+                const double pc = nf_mul(nf_mul(kp.lambda, nf_sub(sr[k], sysh[k0 + k])), r);
+                if (k0 + k == 0) { s1 = pa; s2 = pb; s3 = pc; }
+                else { s1 = nf_add(s1, pa); s2 = nf_add(s2, pb); s3 = nf_add(s3, pc); }
+            }
+            if (d < 8) {
+                for (int k = 0; k < kc; ++k) {
+                    const double p = nf_mul(sr[k], sysh[k0 + k]);
+                    s4 = (k0 + k == 0) ? p : nf_add(s4, p);
+                }
+            } else {
+                int k = 0;
+                for (; k + 8 <= kc && k0 + k + 8 <= d8; k += 8) {
+                    const double p0 = nf_mul(sr[k + 0], sysh[k0 + k + 0]), p1 = nf_mul(sr[k + 1], sysh[k0 + k + 1]);
+                    const double p2 = nf_mul(sr[k + 2], sysh[k0 + k + 2]), p3 = nf_mul(sr[k + 3], sysh[k0 + k + 3]);
+                    const double p4 = nf_mul(sr[k + 4], sysh[k0 + k + 4]), p5 = nf_mul(sr[k + 5], sysh[k0 + k + 5]);
+                    const double p6 = nf_mul(sr[k + 6], sysh[k0 + k + 6]), p7 = nf_mul(sr[k + 7], sysh[k0 + k + 7]);
+                    if (k0 + k == 0) { r0 = p0; r1 = p1; r2 = p2; r3 = p3; r4 = p4; r5 = p5; r6 = p6; r7 = p7; }
+                    else {
+                        r0 = nf_add(r0, p0); r1 = nf_add(r1, p1); r2 = nf_add(r2, p2); r3 = nf_add(r3, p3);
+                        r4 = nf_add(r4, p4); r5 = nf_add(r5, p5); r6 = nf_add(r6, p6); r7 = nf_add(r7, p7);
+                    }
+                }
+                if (k0 + k >= d8 && k < kc) {
+                    if (k0 + k == d8)
+                        s4 = nf_add(nf_add(nf_add(r0, r1), nf_add(r2, r3)), nf_add(nf_add(r4, r5), nf_add(r6, r7)));
+                    for (; k < kc; ++k) s4 = nf_add(s4, nf_mul(sr[k], sysh[k0 + k]));
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < kc; ++k) {
+                const T r = xr[k] - ysh[k0 + k];
+                const T ds = sr[k] - sysh[k0 + k];
+                if (DENSE) {
+                    const T u = xlr[k] - ylsh[k0 + k];
+                    rr = fma_t(u, r, rr);
+                    uu = fma_t(u, u, uu);
+                    su = fma_t(ds, u, su);
+                } else {
+                    rr = fma_t(r, r, rr);
+                    su = fma_t(ds, r, su);
+                }
+                ss = fma_t(sr[k], sysh[k0 + k], ss);
+            }
+        }
+    }
+
+    __device__ __forceinline__ double value(int d, int d8, const KParams& kp) {
+        if constexpr (STRICT) {
+            if (d >= 8) {
+                if (d8 == d) s4 = nf_add(nf_add(nf_add(r0, r1), nf_add(r2, r3)), nf_add(nf_add(r4, r5), nf_add(r6, r7)));
+                s4 = nf_add(0.0, s4);
+            }
+            return strict_finish(s1, s2, s3, s4, kp);
+        } else {
+            return (double)fast_finish<T, DENSE>(rr, uu, su, ss, kp);
+        }
+    }
+};
+
+template <typename T, bool STRICT, bool DENSE, int NST>
+__global__ void __launch_bounds__(kThreads, 1) thin_step_chunked_pipe_kernel(ThinArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char cpm[];
+    const int d = a.kp.d;
+    constexpr int kArr = DENSE ? 3 : 2;
+    T* ysh = reinterpret_cast<T*>(cpm);
+    T* sysh = ysh + d;
+    T* ylsh = sysh + d;
+    T* ring = ylsh + d;                                       // NST x { xt, st, (xlt) } of kThreads x kChunkLd
+
+    const Cand win = pick_winner(a);
+    const long long sel = (long long)win.i;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
+    for (int k = threadIdx.x; k < d; k += kThreads) {
+        ysh[k] = __ldg(a.x + sel * d + k);
+        sysh[k] = __ldg(a.s + sel * d + k);
+        ylsh[k] = DENSE ? __ldg(a.xl + sel * d + k) : T(0);
+    }
+    T lwy = T(0), wy = T(0);
+    if (a.lw) {
+        lwy = __ldg(a.lw + sel);
+        if (!STRICT && a.w) wy = __ldg(a.w + sel);
+    }
+    const long long rows = a.row_end - a.row_begin;
+    const long long stride = (long long)gridDim.x * kThreads;
+    const long long first = (long long)blockIdx.x * kThreads;
+    const long long ntiles = first < rows ? (rows - first + stride - 1) / stride : 0;
+    const int nslabs = (d + kChunkK - 1) / kChunkK;
+    const long long nstages = ntiles * nslabs;
+    const int d8 = d - (d % 8);
+    const int kk = threadIdx.x % kChunkK, rr0 = threadIdx.x / kChunkK;
+
+    auto issue = [&](long long q) {
+        const long long it = q / nslabs;
+        const int k0 = (int)(q - it * nslabs) * kChunkK;
+        const int kc = min(kChunkK, d - k0);
+        const long long base = first + it * stride;
+        const int tile_rows = (int)min((long long)kThreads, rows - base);
+        T* xt = ring + (size_t)(q % NST) * kArr * kThreads * kChunkLd;
+        T* st = xt + kThreads * kChunkLd;
+        T* xlt = st + kThreads * kChunkLd;
+        const long long g0 = (a.row_begin + base + rr0) * d + k0 + kk;
+#pragma unroll
+        for (int j = 0; j < kChunkK; ++j) {
+            const int r = rr0 + j * (kThreads / kChunkK);
+            const bool ok = (kk < kc) && (r < tile_rows);
+            const long long g = g0 + (long long)j * (kThreads / kChunkK) * d;
+            if (ok) {
+                cp_async8(xt + r * kChunkLd + kk, a.x + g);
+                cp_async8(st + r * kChunkLd + kk, a.s + g);
+                if (DENSE) cp_async8(xlt + r * kChunkLd + kk, a.xl + g);
+            } else {
+                xt[r * kChunkLd + kk] = T(0);
+                st[r * kChunkLd + kk] = T(0);
+                if (DENSE) xlt[r * kChunkLd + kk] = T(0);
+            }
+        }
+    };
+
+    for (int q = 0; q < NST - 1; ++q) {                       // prologue: NST - 1 slabs in flight
+        if (q < nstages) issue(q);
+        cp_async_commit_group();                              // (possibly empty) keeps the group count uniform
+    }
+    double bv = __longlong_as_double(0x7ff0000000000000LL);
+    unsigned bi = 0xffffffffu;
+    ChunkRow<T, STRICT, DENSE> row;
+    row.reset();
+    for (long long q = 0; q < nstages; ++q) {
+        if (q + NST - 1 < nstages) issue(q + NST - 1);        // refills the buffer consumed in iteration q - 1
+        cp_async_commit_group();
+        cp_async_wait_group<NST - 1>();                       // slab q has landed (this thread's copies)
+        __syncthreads();                                      // ... and everybody else's; y row visible on the first pass
+        const long long it = q / nslabs;
+        const int slab = (int)(q - it * nslabs);
+        const int k0 = slab * kChunkK;
+        const int kc = min(kChunkK, d - k0);
+        const long long base = first + it * stride;
+        const int tile_rows = (int)min((long long)kThreads, rows - base);
+        const bool active = (int)threadIdx.x < tile_rows;
+        const T* xt = ring + (size_t)(q % NST) * kArr * kThreads * kChunkLd;
+        const T* st = xt + kThreads * kChunkLd;
+        const T* xlt = st + kThreads * kChunkLd;
+        if (active) {
+            if (slab == 0) row.reset();
+            row.slab(xt + threadIdx.x * kChunkLd, st + threadIdx.x * kChunkLd, xlt + threadIdx.x * kChunkLd, ysh, sysh,
+                     ylsh, k0, kc, d, d8, a.kp);
+            if (slab == nslabs - 1) {
+                const long long li = base + threadIdx.x;
+                const long long i = a.row_begin + li;
+                double k = row.value(d, d8, a.kp);
+                double v;
+                const double av = a.A[li];
+                if constexpr (STRICT) {
+                    if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, lwy, wy), k);
+                    v = __dadd_rn(av, __dmul_rn(2.0, k));
+                } else {
+                    v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, lwy, wy), k, av) : fma(2.0, k, av);
+                }
+                a.A[li] = v;
+                if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
+            }
+        }
+        __syncthreads();                                      // buffer q % NST may be overwritten by the next issue
+    }
+    grid_argmin_publish(bv, bi, a);
+}
+
 // ---- all m greedy steps in ONE cooperative launch (single rank, small D) -------------------------------
 // One CTA per SM (or fewer for small shards).  Thread g of the grid owns rows g, g + T, g + 2T, ... for the
 // whole job (T = threads in the grid).  The running objective A and the log-weights of the owned rows live
@@ -876,6 +1089,12 @@ static int tiled_config(int d, bool dense, int& threads, size_t& smem) {
     return GFK_EUNSUPPORTED;
 }
 
+constexpr int kPipeStages = 3;
+template <typename T>
+static size_t chunk_pipe_smem(int d, bool dense) {
+    return sizeof(T) * (size_t)(3 * d + kPipeStages * (dense ? 3 : 2) * kThreads * kChunkLd);
+}
+
 template <typename T, bool STRICT>
 static int launch_step(const ThinArgs<T>& a, int d, cudaStream_t st, int grid_small, int grid_tiled,
                        int tiled_threads, size_t tiled_smem) {
@@ -888,6 +1107,10 @@ static int launch_step(const ThinArgs<T>& a, int d, cudaStream_t st, int grid_sm
         thin_step_small_kernel<T, 1, STRICT, 4><<<grid_small, kThreads, 0, st>>>(a);
     } else if (!dense && d == 3) {
         thin_step_small_kernel<T, 3, STRICT, 2><<<grid_small, kThreads, 0, st>>>(a);
+    } else if (tiled_threads == -1) {
+        const size_t smem = chunk_pipe_smem<T>(d, dense);
+        if (dense) thin_step_chunked_pipe_kernel<T, STRICT, !STRICT, kPipeStages><<<grid_tiled, kThreads, smem, st>>>(a);
+        else thin_step_chunked_pipe_kernel<T, STRICT, false, kPipeStages><<<grid_tiled, kThreads, smem, st>>>(a);
     } else if (tiled_threads == 0) {
         const size_t smem = sizeof(T) * (size_t)(3 * d + (dense ? 3 : 2) * kThreads * kChunkLd);
         if (dense) thin_step_chunked_kernel<T, STRICT, !STRICT><<<grid_tiled, kThreads, smem, st>>>(a);
@@ -1015,7 +1238,18 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     // whole row at once) or y rows too long for its shared memory -> the row-tiled kernel
     const size_t chunked_smem = sizeof(T) * (size_t)(3 * d + (a.xl ? 3 : 2) * kThreads * kChunkLd);
     const bool use_chunked = uses_tiled && !(STRICT && d > 128) && chunked_smem <= 200 * 1024;
-    if (uses_tiled && use_chunked) {
+    bool use_pipe = false;
+    if (const char* penv = getenv("GFK_CHUNK_PIPE")) {
+        use_pipe = penv[0] == '1' && uses_tiled && use_chunked && chunk_pipe_smem<T>(d, a.xl != nullptr) <= 220 * 1024;
+    }
+    if (use_pipe) {
+        const size_t psm = chunk_pipe_smem<T>(d, a.xl != nullptr);
+        if (a.xl) GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_pipe_kernel<T, STRICT, !STRICT, kPipeStages>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        else GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_pipe_kernel<T, STRICT, false, kPipeStages>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        tiled_threads = -1;                          // launch_step: the pipelined kernel
+    } else if (uses_tiled && use_chunked) {
         if (a.xl) GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_kernel<T, STRICT, !STRICT>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunked_smem));
         else GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_kernel<T, STRICT, false>,
@@ -1042,6 +1276,7 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     const int grid_init = grid_for(kThreads, 8);
     const int grid_small = grid_for(kThreads * 2, 4);
     const int grid_tiled = !uses_tiled ? 1
+                           : use_pipe ? grid_for(kThreads, 1)
                            : use_chunked ? grid_for(kThreads, chunked_smem > 72 * 1024 ? 2 : 3)
                                          : grid_for(tiled_threads, tiled_smem > 50 * 1024 ? 2 : 4);
 

@@ -31,7 +31,22 @@ __global__ void early_exit_kernel(int* out, int n) {
     out[threadIdx.x] = (int)present;
 }
 
+// cp.async staging; with_wait = 0 reads the staged value without cp.async.wait_group
+__global__ void async_copy_kernel(const double* src, double* out, int with_wait) {
+    extern __shared__ double stage[];
+    simt::cp_async(&stage[threadIdx.x], src + threadIdx.x, 8);
+    simt::cp_async_commit();
+    if (with_wait) simt::cp_async_wait(0);
+    __syncthreads();
+    out[threadIdx.x] = stage[(threadIdx.x + 1) % blockDim.x];
+}
+
 }  // namespace
+
+extern "C" int simt_selftest_async_copy(const double* src, double* out, int with_wait) {
+    async_copy_kernel<<<1, 64, 64 * sizeof(double)>>>(src, out, with_wait);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int simt_selftest_divergent_barrier(void) {
     int storage[64] = {0};

@@ -74,6 +74,9 @@ struct Fiber {
     int warp = 0, lane = 0;
     unsigned last_mask = 0;
     int wait_id = 0;
+    struct Copy { void* dst; const void* src; int bytes; };
+    std::vector<std::vector<Copy>> groups;    // committed cp.async groups, oldest first
+    std::vector<Copy> open_group;             // copies issued since the last commit
 };
 
 struct Block {
@@ -222,6 +225,32 @@ const unsigned long long* warp_gather(unsigned long long bits) {
 // the lanes that took part in this thread's most recent collective (lanes that exit later must still count)
 unsigned warp_alive_mask() { return t_blk->running->last_mask; }
 
+void cp_async(void* dst, const void* src, int bytes) {
+    Fiber* f = t_blk->running;
+    check_align(dst, (size_t)bytes, "cp.async destination");
+    check_align(src, (size_t)bytes, "cp.async source");
+    f->open_group.push_back(Fiber::Copy{dst, src, bytes});
+}
+
+void cp_async_commit() {
+    Fiber* f = t_blk->running;
+    f->groups.push_back(std::move(f->open_group));
+    f->open_group.clear();
+}
+
+static void run_copies(std::vector<Fiber::Copy>& g) {
+    for (const Fiber::Copy& c : g) memcpy(c.dst, c.src, (size_t)c.bytes);
+    g.clear();
+}
+
+void cp_async_wait(int allow_pending_groups) {
+    Fiber* f = t_blk->running;
+    while ((int)f->groups.size() > allow_pending_groups) {
+        run_copies(f->groups.front());
+        f->groups.erase(f->groups.begin());
+    }
+}
+
 void poll_yield() {
     Block* b = t_blk;
     if (!b || !b->running) return;
@@ -236,6 +265,9 @@ static void fiber_main() {
     Block* b = t_blk;
     (*b->fn)();
     Fiber* f = b->running;
+    for (auto& g : f->groups) run_copies(g);                    // the hardware completes them; nobody may rely on it
+    f->groups.clear();
+    run_copies(f->open_group);
     f->done = true;
     WarpState& w = b->warps[f->warp];
     b->alive--;
@@ -305,6 +337,8 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
         f.ctx.gdim = uint3{grid.x, grid.y, grid.z};
         f.wait = W_NONE;
         f.done = false;
+        f.groups.clear();
+        f.open_group.clear();
         f.warp = t / 32;
         f.lane = t % 32;
         WarpState& w = b.warps[(size_t)f.warp];

@@ -60,6 +60,12 @@ void named_barrier(int id, int count, bool wait);
 const unsigned long long* warp_gather(unsigned long long bits);
 unsigned warp_alive_mask();
 void poll_yield();                      // inside spin loops on memory another thread writes
+// cp.async with its real (deferred) semantics: the bytes move no earlier than the cp_async_wait that covers their
+// group, so reading a staged buffer before waiting - or before the barrier that publishes OTHER threads' waits -
+// finds the poison pattern instead of data
+void cp_async(void* dst, const void* src, int bytes);
+void cp_async_commit();
+void cp_async_wait(int allow_pending_groups);
 [[noreturn]] void fail(const char* fmt, ...);
 void check_align(const void* p, size_t a, const char* what);
 

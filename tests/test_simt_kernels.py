@@ -397,6 +397,13 @@ def test_emulator_reports_deliberate_defects():
         wrong += int(not np.array_equal(out, want))
     assert wrong == 3                                                     # without it: caught under every seed
     H.set_schedule(False)
+    # cp.async is deferred like on the device: data read before cp.async.wait_group is the poison pattern, not data
+    src, got = np.arange(64, dtype=np.float64), np.zeros(64)
+    PD = ctypes.POINTER(ctypes.c_double)
+    assert lib.simt_selftest_async_copy(src.ctypes.data_as(PD), got.ctypes.data_as(PD), 1) == 0
+    assert np.array_equal(got, np.roll(src, -1))
+    assert lib.simt_selftest_async_copy(src.ctypes.data_as(PD), got.ctypes.data_as(PD), 0) == 0
+    assert np.isnan(got).sum() >= 60            # (a thread that has already exited has had its copies completed)
     for n in (64, 40, 33, 7):
         out = np.full(64, -1, dtype=np.int32)
         assert lib.simt_selftest_early_exit(out.ctypes.data_as(P), n) == 0
@@ -533,3 +540,37 @@ def test_warp_specialised_ksd_kernel_equals_the_tile_kernel(d, monkeypatch):
             H.set_schedule(False)
     ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med')
     np.testing.assert_allclose(H.SimProblem(x, g, log_p, log_q, preconditioner='med').ksd(), os_.ksd(ref, n), rtol=1e-10)
+
+
+@pytest.mark.parametrize('d', [5, 8, 9, 16, 17, 33, 64, 100])
+def test_pipelined_step_kernel_equals_the_slab_kernel(d, monkeypatch):
+    """GFK_CHUNK_PIPE=1: thin_step_chunked_pipe_kernel (three slabs in flight per CTA) must select the oracle's indices
+    and leave bit-identical objectives to thin_step_chunked_kernel, in every precision, under any thread schedule."""
+    monkeypatch.setenv('GFK_PERSISTENT', '0')
+    monkeypatch.setenv('SIMT_SMS', '2')                          # 2 CTAs x 256 rows: several tiles per CTA
+    rng = np.random.default_rng(9000 + d)
+    x, g = _mcmc_like(rng, 1333, d)
+    log_p = -0.5 * np.sum(x ** 2, axis=1) / d
+    log_q = log_p + 0.5 * np.sin(x[:, 0])
+    m = 9
+    expect = ot.thin_gf(x, log_p, log_q, g, m, preconditioner='med')
+    for precision in ('f64', 'f64-fast', 'f32'):
+        monkeypatch.delenv('GFK_CHUNK_PIPE', raising=False)
+        base = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(m)
+        monkeypatch.setenv('GFK_CHUNK_PIPE', '1')
+        for random, seed in ((False, 0), (True, 5)):
+            H.set_schedule(random, seed)
+            idx, obj = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(m)
+            assert np.array_equal(idx, base[0]) and np.array_equal(obj, base[1]), (precision, random)
+        H.set_schedule(False)
+        if precision != 'f32':
+            assert np.array_equal(base[0], expect), precision
+    # dense preconditioner: the pipelined kernel does not fit three 3-array slabs and must fall back, not fail
+    a = rng.standard_normal((d, d))
+    dense = a @ a.T / d + np.eye(d)
+    p = H.SimProblem(x[:300], g[:300], preconditioner=dense, precision='f64-fast')
+    monkeypatch.delenv('GFK_CHUNK_PIPE', raising=False)
+    want = p.thin(4)
+    monkeypatch.setenv('GFK_CHUNK_PIPE', '1')
+    got = p.thin(4)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
