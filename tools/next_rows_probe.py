@@ -52,6 +52,19 @@ for n in (50_000, 200_000):
         os.environ.pop('GFK_KSD_WS', None)
     del p
 
+# C5-shaped step kernel (d = 64): slab kernel vs the opt-in three-stage cp.async pipeline
+c = synthetic.config_c5(n=500_000, m=40)
+for prec in ('f64', 'f64-fast', 'f32'):
+    for pipe in ('0', '1'):
+        os.environ['GFK_CHUNK_PIPE'] = pipe
+        p = SteinProblem(c['sample'], c['gradient'], preconditioner='med', precision=prec)
+        idx = p.thin(40)
+        t = timed(lambda: p.thin(40), reps=2)
+        note(f'c5_step:{prec}:pipe{pipe}', us_per_step=t / 40 * 1e6, hbm_floor_us=500_000 * (1040 if prec != 'f32' else 528) / 6547.2e3,
+             idx_head=[int(v) for v in idx[:6]])
+    os.environ.pop('GFK_CHUNK_PIPE', None)
+del p
+
 # section 8f kernels
 rng = np.random.default_rng(0)
 for n, d in ((100_000, 4), (200_000, 2)):
