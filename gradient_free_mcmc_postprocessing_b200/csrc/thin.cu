@@ -858,6 +858,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     const long long TT = (long long)gridDim.x * nthr;
     const long long gt = (long long)blockIdx.x * nthr + tid;
     const long long rows = a.row_end - a.row_begin;
+    // Row ownership: pass j < rpt - 1 gives thread g of the grid row j * TT + g (coalesced, every thread busy).  The
+    // LAST pass is usually partial; dealing its rows to the first threads of the grid would hand whole CTAs one more
+    // row per thread than others (measured: CTAs 0-29 of 148 finish C3's update ~1.9 us after the rest, and every step
+    // waits for the slowest CTA).  Its rows are dealt round-robin over the CTAs instead, so all SMs carry the same load.
+    const long long last_base = (long long)(rpt - 1) * TT;
+    const long long last_e = (long long)tid * gridDim.x + blockIdx.x;
     const int slots = rpt * nthr;
     double* A_sh = reinterpret_cast<double*>(psm);
     T* lw_sh = reinterpret_cast<T*>(A_sh + slots);              // lw (strict / no w) or w (fast)
@@ -872,7 +878,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     double bv = __longlong_as_double(0x7ff0000000000000LL);
     unsigned bi = 0xffffffffu;
     for (int j = 0; j < rpt; ++j) {
-        const long long li = (long long)j * TT + gt;
+        const long long li = (j == rpt - 1) ? last_base + last_e : (long long)j * TT + gt;
         const int slot = j * nthr + tid;
         if (li < rows) {
             const long long i = a.row_begin + li;
@@ -1011,7 +1017,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         GFK_STAMP(step + 1, 0);
 #pragma unroll 2
         for (int j = 0; j < rpt; ++j) {
-            const long long li = (long long)j * TT + gt;
+            const long long li = (j == rpt - 1) ? last_base + last_e : (long long)j * TT + gt;
             const int slot = j * nthr + tid;
             if (li < rows) {
                 const long long i = a.row_begin + li;
@@ -1046,7 +1052,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     }
     // ---- write the running objective back -----------------------------------------------------------
     for (int j = 0; j < rpt; ++j) {
-        const long long li = (long long)j * TT + gt;
+        const long long li = (j == rpt - 1) ? last_base + last_e : (long long)j * TT + gt;
         if (li < rows) a.A[li] = A_sh[j * nthr + tid];
     }
 }
