@@ -12,6 +12,13 @@ echo "== bench"; timeout 400 python bench.py > gpurun_out/bench_n1.log 2> gpurun
 echo "== bench reference arm"; timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; echo "rc=$?"
 echo "== probes"; timeout 400 python tools/gpu_probe.py > gpurun_out/probe.log 2>&1; echo "rc=$?"
 timeout 400 python tools/next_rows_probe.py > gpurun_out/next_rows_probe.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/next_rows_probe.log
+echo "== per-phase trace of the persistent kernel (needs: GFK_TRACE=1 bash gradient_free_mcmc_postprocessing_b200/csrc/build.sh)"
+if [ -f libgfk_trace.so ]; then
+    for cfg in "c3 f64" "c3 f64-fast" "c2 f64"; do
+        GFK_LIB=$PWD/libgfk_trace.so timeout 200 python tools/trace_steps.py $cfg >> gpurun_out/trace.log 2>&1
+    done
+    tail -30 gpurun_out/trace.log
+fi
 echo "== ncu launch list of the bench"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/bench_launches_ncu.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "rc=$?"
