@@ -167,8 +167,13 @@ using namespace gfk;
 
 extern "C" size_t gfk_energy_ws_bytes(int64_t n, int64_t m) {
     if (n < 1 || m < 1) return 0;
-    const int64_t rows = n > m ? n : m;
-    return sizeof(double) * (size_t)(n + 2 * m + (int64_t)kEnMaxSplits * rows);
+    // xx[n], cross[m], low[m], then the split partials of the largest of the three row-sum launches
+    const int64_t p_xx = (int64_t)en_splits(n, n) * n;
+    const int64_t p_cross = (int64_t)en_splits(m, n) * m;
+    const int64_t p_low = (int64_t)en_splits(m, m) * m;
+    int64_t partial = p_xx > p_cross ? p_xx : p_cross;
+    if (p_low > partial) partial = p_low;
+    return sizeof(double) * (size_t)(n + 2 * m + partial);
 }
 
 extern "C" int gfk_energy_distance_cumulative(const double* x, int64_t n, const double* y, int64_t m, int32_t d,
