@@ -15,7 +15,7 @@ from ._lib import Problem, check
 
 WEIGHT_SCALE_THRESHOLD = 10     # stein_thinning.thinning.WEIGHT_SCALE_THRESHOLD
 MEDIAN_SUBSAMPLE = 1000         # rows entering the median heuristic
-KSD_PREEXP_LIMIT = 300.0        # |lw| below this: exp(lw_i) exp(lw_j) cannot leave the normal range of float64
+EXP_DD_LIMIT = 350.0            # kExpDdLimit of csrc/stein_math.cuh: |lw| up to which the strict mode pre-exponentiates
 
 
 def _require_cuda(device):
@@ -241,6 +241,17 @@ class SteinProblem:
         if self.gf and self.mode != _lib.F64_STRICT:
             self.w = torch.empty_like(klw)
             check(lib.gfk_exp_weights(_ptr(klw), _ptr(self.w), self.n, int(self.mode == _lib.F32_FAST), st))
+        elif self.gf:
+            # strict mode: per-row double-double exp(lw) so that the pair weight exp(fl(lw_i + lw_j)) costs 12 IEEE
+            # operations, is correctly rounded and machine independent (csrc/stein_math.cuh exp_sum_dd) - unless a
+            # log-weight is so large that exp(lw_i) alone could overflow or go subnormal; then the device exp stays
+            rng = (ctypes.c_double * 2)()
+            ws = _bytes(lib.gfk_log_weights_ws_bytes(), self.device)
+            check(lib.gfk_log_weights_range(_ptr(klw), self.n, rng, _ptr(ws), st))
+            self.lw_range = (rng[0], rng[1])
+            if -EXP_DD_LIMIT <= rng[0] and rng[1] <= EXP_DD_LIMIT:
+                self.w = torch.empty((self.n, 2), dtype=torch.float64, device=self.device)
+                check(lib.gfk_exp_weights_dd(_ptr(klw), _ptr(self.w), self.n, st))
         self._kx, self._ks, self._klw, self._kxl = kx, ks, klw, kxl
         self.struct = Problem(x=kx.data_ptr(), s=ks.data_ptr(),
                               lw=klw.data_ptr() if klw is not None else None,
@@ -290,28 +301,6 @@ class SteinProblem:
             raise IndexError('selection indices out of range')
         return torch.from_numpy(sel.astype(np.uint32).view(np.int32)).to(self.device)
 
-    def _ksd_struct(self):
-        """The problem as the KSD row-sum kernel reads it.  KSD values carry no bit-for-bit claim (1e-10 relative), so
-        the strict mode also multiplies by pre-exponentiated weights w_i w_j instead of evaluating exp(lw_i + lw_j)
-        per pair (~30 of ~100 FP64 instructions per pair at d = 10) - unless a log-weight is so large that exp(lw_i)
-        alone could overflow or lose precision to underflow where exp(lw_i + lw_j) would not."""
-        if not self.gf or self.w is not None:
-            return self.struct
-        if getattr(self, '_struct_ksd', None) is None:
-            lib = _lib.load()
-            st = _stream_ptr(self.device)
-            rng = (ctypes.c_double * 2)()
-            ws = _bytes(lib.gfk_log_weights_ws_bytes(), self.device)
-            check(lib.gfk_log_weights_range(_ptr(self._klw), self.n, rng, _ptr(ws), st))
-            if -KSD_PREEXP_LIMIT <= rng[0] and rng[1] <= KSD_PREEXP_LIMIT:
-                self._w_ksd = torch.empty_like(self._klw)
-                check(lib.gfk_exp_weights(_ptr(self._klw), _ptr(self._w_ksd), self.n, 0, st))
-                self._struct_ksd = Problem.from_buffer_copy(self.struct)
-                self._struct_ksd.w = self._w_ksd.data_ptr()
-            else:
-                self._struct_ksd = self.struct
-        return self._struct_ksd
-
     def ksd(self, sel=None, m=None):
         """Cumulative KSD over rows ``sel`` (or the first ``m`` rows); float64 ndarray of length m."""
         lib = _lib.load()
@@ -322,7 +311,7 @@ class SteinProblem:
             low = torch.empty(m, dtype=torch.float64, device=self.device)
             diag = torch.empty(m, dtype=torch.float64, device=self.device)
             ks = torch.empty(m, dtype=torch.float64, device=self.device)
-            check(lib.gfk_ksd_rowsums(ctypes.byref(self._ksd_struct()), _ptr(sel_dev), m, lib.gfk_comm_rank(),
+            check(lib.gfk_ksd_rowsums(ctypes.byref(self.struct), _ptr(sel_dev), m, lib.gfk_comm_rank(),
                                       lib.gfk_comm_size(), _ptr(low), _ptr(diag), st))
             if lib.gfk_comm_size() > 1:
                 check(lib.gfk_allreduce_sum(_ptr(low), m, st))

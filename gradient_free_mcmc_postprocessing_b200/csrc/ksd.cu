@@ -32,6 +32,7 @@ struct KsdArgs {
     const uint32_t* sel;
     long long m;
     KParams kp;
+    int wstride;        // elements between consecutive rows' weights in w: 1 (fast modes), 2 (strict: (hi, lo) pairs)
     int part, n_parts;
     double* low;
     double* diag;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
         if (k0 == 0 && threadIdx.x < TILE) {
             const long long t = c0 + threadIdx.x;
             T v = T(0);
-            if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
+            if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t) * a.wstride) : __ldg(a.lw + row_of(a, t));
             wcb[(J & 1) * TILE + threadIdx.x] = v;
         }
         cp_async_commit();
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
     if (threadIdx.x < TILE) {
         const long long t = t0 + threadIdx.x;
         T v = T(0);
-        if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
+        if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t) * a.wstride) : __ldg(a.lw + row_of(a, t));
         wr[threadIdx.x] = v;
     }
     if (single_chunk) {   // the row tile is invariant over J: stage it once (buffer 0's row slots)
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(KSD_WS_THREADS) ksd_rowsum_ws_kernel(KsdArgs<T
     if (tid < TILE) {
         const long long t = t0 + tid;
         T v = T(0);
-        if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
+        if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t) * a.wstride) : __ldg(a.lw + row_of(a, t));
         wr[tid] = v;
     }
     cp_async_commit();
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(KSD_WS_THREADS) ksd_rowsum_ws_kernel(KsdArgs<T
             for (int r = lane; r < TILE; r += 32) {
                 const long long t = c0 + r;
                 T v = T(0);
-                if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t)) : __ldg(a.lw + row_of(a, t));
+                if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t) * a.wstride) : __ldg(a.lw + row_of(a, t));
                 wcb[b * TILE + r] = v;
             }
             cp_async_commit();
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(256) ksd_diag_kernel(KsdArgs<T> a) {
         }
         double kd = (double)k;
         if (a.lw) {
-            if (a.w) { const T wv = __ldg(a.w + i); kd = (double)(k * (wv * wv)); }
+            if (a.w) { const T wv = __ldg(a.w + i * a.wstride); kd = (double)(k * (wv * wv)); }
             else { const double l = (double)__ldg(a.lw + i); kd *= exp(l + l); }
         }
         a.diag[t] = kd;
@@ -472,7 +473,16 @@ __device__ __forceinline__ double eval_pair(const KsdArgs<T>& a, long long i, lo
     double k;
     if constexpr (STRICT) {
         k = pair_strict<0>(xi, xj, si, sj, a.kp);
-        if (a.lw) k = __dmul_rn(exp(__dadd_rn((double)a.lw[i], (double)a.lw[j])), k);
+        if (a.lw) {
+            double wgt;
+            if (a.w) {     // strict mode: double-double exponentials (hi, lo) per row, the weight of the thinning kernels
+                wgt = exp_sum_dd((double)a.lw[i], (double)a.lw[j], (double)a.w[2 * i], (double)a.w[2 * i + 1],
+                                 (double)a.w[2 * j], (double)a.w[2 * j + 1]);
+            } else {
+                wgt = exp(__dadd_rn((double)a.lw[i], (double)a.lw[j]));
+            }
+            k = __dmul_rn(wgt, k);
+        }
     } else {
         if (a.xl) {
             GView<T> li{a.xl + i * d}, lj{a.xl + j * d};
@@ -480,7 +490,7 @@ __device__ __forceinline__ double eval_pair(const KsdArgs<T>& a, long long i, lo
         } else {
             k = (double)pair_fast<T, 0, false>(xi, xj, si, sj, xi, xj, a.kp);
         }
-        if (a.lw) k *= a.w ? (double)(a.w[i] * a.w[j]) : exp((double)a.lw[i] + (double)a.lw[j]);
+        if (a.lw) k *= a.w ? (double)(a.w[i * a.wstride] * a.w[j * a.wstride]) : exp((double)a.lw[i] + (double)a.lw[j]);
     }
     return k;
 }
@@ -518,6 +528,7 @@ static KsdArgs<T> make_args(const gfk_problem* p, const uint32_t* sel, int64_t m
     a.sel = sel;
     a.m = m;
     a.kp = KParams{p->lambda, p->lambda_sq, p->trace, p->c, p->d, p->xl != nullptr};
+    a.wstride = (p->mode == GFK_F64_STRICT) ? 2 : 1;
     a.part = 0;
     a.n_parts = 1;
     a.low = nullptr;

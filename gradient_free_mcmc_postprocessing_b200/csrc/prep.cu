@@ -206,6 +206,24 @@ __global__ void exp_weights_kernel(const T* __restrict__ lw, T* __restrict__ w, 
         w[e] = (T)exp((double)lw[e]);
 }
 
+// ew[2 i], ew[2 i + 1] = double-double exp(lw_i) for the strict-mode weights (stein_math.cuh exp_dd); rows with
+// |lw| beyond kExpDdLimit are never used this way (the host checks the range first) and get NaN markers
+__global__ void exp_weights_dd_kernel(const double* __restrict__ lw, double* __restrict__ ew, long long count) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count;
+         e += (long long)gridDim.x * blockDim.x) {
+        const double l = lw[e];
+        double hi, lo;
+        if (fabs(l) <= kExpDdLimit) {
+            exp_dd(l, hi, lo);
+        } else {
+            hi = __longlong_as_double(0x7ff8000000000000LL);
+            lo = hi;
+        }
+        ew[2 * e] = hi;
+        ew[2 * e + 1] = lo;
+    }
+}
+
 // lw = log_q - log_p; optional range cap: lw = max(lw - max(lw), -cap).  Two launches: (min, max, NaN) then apply.
 __global__ void __launch_bounds__(256) lw_minmax_kernel(const double* __restrict__ log_p,
                                                         const double* __restrict__ log_q, long long n,
@@ -398,6 +416,16 @@ extern "C" int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f3
     else
         exp_weights_kernel<double><<<grid_for(count, 256), 256, 0, st>>>(static_cast<const double*>(lw),
                                                                          static_cast<double*>(w), count);
+    count_launches(1);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" int gfk_exp_weights_dd(const double* lw, double* ew, int64_t count, void* stream) {
+    GFK_REQUIRE(lw && ew && count >= 0, "gfk_exp_weights_dd: bad arguments");
+    GFK_REQUIRE(reinterpret_cast<uintptr_t>(ew) % 16 == 0, "gfk_exp_weights_dd: ew must be 16-byte aligned");
+    if (count == 0) return GFK_OK;
+    exp_weights_dd_kernel<<<grid_for(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(lw, ew, count);
     count_launches(1);
     GFK_CHECK_LAUNCH();
     return GFK_OK;

@@ -309,6 +309,83 @@ GFK_HD T pair_fast(const AX& x, const AY& y, const ASX& sx, const ASY& sy, const
     return fast_finish<T, DENSE>(rr, uu, su, ss, kp);
 }
 
+// ---- gradient-free weights in the strict mode: exp(lw_i + lw_j) without a device exp ---------------------------
+// numpy evaluates exp(fl(lw_i + lw_j)) per pair.  The device's exp() is accurate to 1 ulp, not correctly rounded,
+// costs ~30 FP64 instructions plus as many constant moves per pair, and differs from the host's.  Instead every row
+// gets E_i = exp(lw_i) ONCE per job as a double-double (exp_dd: argument reduction, Taylor polynomial and eight
+// squarings in double-double arithmetic - IEEE operations only, so the result is the same on any machine, accurate
+// to ~2^-96), and a pair costs 12 IEEE operations (exp_sum_dd):
+//   a + b = s + err exactly (TwoSum),  exp(s) = E_a E_b exp(-err) = (E_a E_b)(1 - err) up to err^2 ~ 2^-86,
+// i.e. exp(fl(a + b)) correctly rounded in all but ~2^-30 of the cases.  Valid while |a|, |b| <= kExpDdLimit (no
+// overflow, no subnormal parts); outside that range the caller keeps the device exp.
+constexpr double kExpDdLimit = 350.0;
+
+GFK_HD void two_sum(double a, double b, double& s, double& e) {
+    s = nf_add(a, b);
+    const double bb = nf_sub(s, a);
+    e = nf_add(nf_sub(a, nf_sub(s, bb)), nf_sub(b, bb));
+}
+GFK_HD void quick_two_sum(double a, double b, double& s, double& e) {      // |a| >= |b|
+    s = nf_add(a, b);
+    e = nf_sub(b, nf_sub(s, a));
+}
+GFK_HD void dd_mul(double ah, double al, double bh, double bl, double& ch, double& cl) {
+    const double p = nf_mul(ah, bh);
+    double e = nf_fma(ah, bh, -p);
+    e = nf_fma(ah, bl, e);
+    e = nf_fma(al, bh, e);
+    quick_two_sum(p, e, ch, cl);
+}
+GFK_HD void dd_add(double ah, double al, double bh, double bl, double& ch, double& cl) {
+    double s, e;
+    two_sum(ah, bh, s, e);
+    e = nf_add(e, nf_add(al, bl));
+    quick_two_sum(s, e, ch, cl);
+}
+
+// (hi, lo) with hi + lo = exp(l) to ~2^-96 relative, |l| <= kExpDdLimit
+GFK_HD void exp_dd(double l, double& hi, double& lo) {
+    const double LN2_H = 0.6931471805599453, LN2_L = 2.3190468138462996e-17, LOG2E = 1.4426950408889634;
+    // 1 / n! as double-doubles, n = 0 .. 11
+    const double CH[12] = {1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333,
+                           0.001388888888888889, 0.0001984126984126984, 2.48015873015873e-05,
+                           2.7557319223985893e-06, 2.755731922398589e-07, 2.505210838544172e-08};
+    const double CL[12] = {0.0, 0.0, 0.0, 9.25185853854297e-18, 2.3129646346357427e-18, 1.1564823173178714e-19,
+                           -5.300543954373577e-20, 1.7209558293420705e-22, 2.1511947866775882e-23,
+                           -1.858393274046472e-22, 2.3767714622250297e-23, -1.448814070935912e-24};
+    const double kf = rint(nf_mul(l, LOG2E));
+    // r = l - k ln2 as a double-double (k ln2_h is formed exactly, |k| < 2^10)
+    const double ph = nf_mul(kf, LN2_H);
+    double pl = nf_fma(kf, LN2_H, -ph);
+    pl = nf_fma(kf, LN2_L, pl);
+    double rh, rl;
+    two_sum(l, -ph, rh, rl);
+    rl = nf_sub(rl, pl);
+    quick_two_sum(rh, rl, rh, rl);
+    rh = nf_mul(rh, 0.00390625);                                          // r / 256: |r'| <= 1.36e-3
+    rl = nf_mul(rl, 0.00390625);
+    double sh = CH[11], sl = CL[11];
+    for (int n = 10; n >= 0; --n) {
+        dd_mul(sh, sl, rh, rl, sh, sl);
+        dd_add(sh, sl, CH[n], CL[n], sh, sl);
+    }
+    for (int j = 0; j < 8; ++j) dd_mul(sh, sl, sh, sl, sh, sl);           // exp(r) = exp(r / 256)^256
+    const int k = (int)kf;
+    hi = ldexp(sh, k);
+    lo = ldexp(sl, k);
+}
+
+// exp(fl(a + b)) from E_a = (eah, eal) ~ exp(a) and E_b = (ebh, ebl) ~ exp(b)
+GFK_HD double exp_sum_dd(double a, double b, double eah, double eal, double ebh, double ebl) {
+    double s, err;
+    two_sum(a, b, s, err);                                               // numpy's exponent is s; a + b = s + err
+    const double p = nf_mul(eah, ebh);
+    double pl = nf_fma(eah, ebh, -p);
+    pl = nf_fma(eah, ebl, pl);
+    pl = nf_fma(eal, ebh, pl);
+    return nf_add(p, nf_fma(-p, err, pl));
+}
+
 // ---- (value, index) with numpy.argmin semantics ---------------------------------------------------
 // smaller value wins; NaN beats every number (np.argmin returns the first NaN); ties -> lower index
 struct Cand {

@@ -299,10 +299,47 @@ __device__ __forceinline__ void grid_argmin_publish(double v, unsigned i, const 
     }
 }
 
+// gradient-free weight state of the selected row y.  Strict mode: a.w, when present, holds double-double
+// exponentials (hi, lo) per row (gfk_exp_weights_dd) and the weight is exp_sum_dd (stein_math.cuh) - IEEE operations
+// only; without it the device exp() is used.  Fast modes: a.w holds plain exp(lw) and the weight is a product.
+template <typename T>
+struct YWeight {
+    T lw, w;
+    double eh, el;
+};
+
 template <typename T, bool STRICT>
-__device__ __forceinline__ double weight_pair(const ThinArgs<T>& a, long long i, T lwy, T wy) {
-    if (STRICT || a.w == nullptr) return exp((double)__ldg(a.lw + i) + (double)lwy);
-    return (double)(__ldg(a.w + i) * wy);
+__device__ __forceinline__ YWeight<T> load_yweight(const ThinArgs<T>& a, long long sel) {
+    YWeight<T> y;
+    y.lw = T(0); y.w = T(0); y.eh = 0.0; y.el = 0.0;
+    if (a.lw) {
+        y.lw = __ldg(a.lw + sel);
+        if constexpr (STRICT) {
+            if (a.w) {
+                const double2 e = __ldg(reinterpret_cast<const double2*>(a.w) + sel);
+                y.eh = e.x;
+                y.el = e.y;
+            }
+        } else {
+            if (a.w) y.w = __ldg(a.w + sel);
+        }
+    }
+    return y;
+}
+
+template <typename T, bool STRICT>
+__device__ __forceinline__ double weight_pair(const ThinArgs<T>& a, long long i, const YWeight<T>& y) {
+    if constexpr (STRICT) {
+        const double lwi = (double)__ldg(a.lw + i);
+        if (a.w) {
+            const double2 e = __ldg(reinterpret_cast<const double2*>(a.w) + i);
+            return exp_sum_dd(lwi, (double)y.lw, e.x, e.y, y.eh, y.el);
+        }
+        return exp(lwi + (double)y.lw);
+    } else {
+        if (a.w == nullptr) return exp((double)__ldg(a.lw + i) + (double)y.lw);
+        return (double)(__ldg(a.w + i) * y.w);
+    }
 }
 
 // ---- step 0: A_i = k(x_i, x_i) (generic runtime-d, not on the critical path) -----------------------
@@ -328,10 +365,9 @@ __global__ void __launch_bounds__(kThreads) thin_init_kernel(ThinArgs<T> a) {
             }
         }
         if (a.lw) {
-            const T lwi = __ldg(a.lw + i);
-            const T wi = (!STRICT && a.w) ? __ldg(a.w + i) : T(0);
-            k = STRICT ? __dmul_rn(weight_pair<T, STRICT>(a, i, lwi, wi), k)
-                       : weight_pair<T, STRICT>(a, i, lwi, wi) * k;
+            const YWeight<T> self = load_yweight<T, STRICT>(a, i);
+            k = STRICT ? __dmul_rn(weight_pair<T, STRICT>(a, i, self), k)
+                       : weight_pair<T, STRICT>(a, i, self) * k;
         }
         a.A[li] = k;
         if (cand_better(k, (unsigned)i, bv, bi)) { bv = k; bi = (unsigned)i; }
@@ -348,11 +384,7 @@ __global__ void __launch_bounds__(kThreads) thin_step_small_kernel(ThinArgs<T> a
     T y[D], sy[D];
     load_row<D>(a.x, sel, y);
     load_row<D>(a.s, sel, sy);
-    T lwy = T(0), wy = T(0);
-    if (a.lw) {
-        lwy = __ldg(a.lw + sel);
-        if (!STRICT && a.w) wy = __ldg(a.w + sel);
-    }
+    const YWeight<T> yw = load_yweight<T, STRICT>(a, sel);
     double bv = __longlong_as_double(0x7ff0000000000000LL);
     unsigned bi = 0xffffffffu;
     const long long rows = a.row_end - a.row_begin;
@@ -369,7 +401,7 @@ __global__ void __launch_bounds__(kThreads) thin_step_small_kernel(ThinArgs<T> a
                 load_row<D>(a.x, i, xr[j]);
                 load_row<D>(a.s, i, sr[j]);
                 av[j] = a.A[li];
-                wt[j] = a.lw ? weight_pair<T, STRICT>(a, i, lwy, wy) : 1.0;
+                wt[j] = a.lw ? weight_pair<T, STRICT>(a, i, yw) : 1.0;
             }
         }
 #pragma unroll
@@ -419,11 +451,7 @@ __global__ void thin_step_tiled_kernel(ThinArgs<T> a) {
         sysh[k] = __ldg(a.s + sel * d + k);
         ylsh[k] = dense ? __ldg(a.xl + sel * d + k) : T(0);
     }
-    T lwy = T(0), wy = T(0);
-    if (a.lw) {
-        lwy = __ldg(a.lw + sel);
-        if (!STRICT && a.w) wy = __ldg(a.w + sel);
-    }
+    const YWeight<T> yw = load_yweight<T, STRICT>(a, sel);
     double bv = __longlong_as_double(0x7ff0000000000000LL);
     unsigned bi = 0xffffffffu;
     const long long rows = a.row_end - a.row_begin;
@@ -457,10 +485,10 @@ __global__ void thin_step_tiled_kernel(ThinArgs<T> a) {
             double v;
             const double av = a.A[li];
             if constexpr (STRICT) {
-                if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, lwy, wy), k);
+                if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, yw), k);
                 v = __dadd_rn(av, __dmul_rn(2.0, k));
             } else {
-                v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, lwy, wy), k, av) : fma(2.0, k, av);
+                v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, yw), k, av) : fma(2.0, k, av);
             }
             a.A[li] = v;
             if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
@@ -496,11 +524,7 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
         sysh[k] = __ldg(a.s + sel * d + k);
         ylsh[k] = DENSE ? __ldg(a.xl + sel * d + k) : T(0);
     }
-    T lwy = T(0), wy = T(0);
-    if (a.lw) {
-        lwy = __ldg(a.lw + sel);
-        if (!STRICT && a.w) wy = __ldg(a.w + sel);
-    }
+    const YWeight<T> yw = load_yweight<T, STRICT>(a, sel);
     double bv = __longlong_as_double(0x7ff0000000000000LL);
     unsigned bi = 0xffffffffu;
     const long long rows = a.row_end - a.row_begin;
@@ -610,10 +634,10 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
             double v;
             const double av = a.A[li];
             if constexpr (STRICT) {
-                if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, lwy, wy), k);
+                if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, yw), k);
                 v = __dadd_rn(av, __dmul_rn(2.0, k));
             } else {
-                v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, lwy, wy), k, av) : fma(2.0, k, av);
+                v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, yw), k, av) : fma(2.0, k, av);
             }
             a.A[li] = v;
             if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
@@ -746,11 +770,7 @@ __global__ void __launch_bounds__(kThreads, 1) thin_step_chunked_pipe_kernel(Thi
         sysh[k] = __ldg(a.s + sel * d + k);
         ylsh[k] = DENSE ? __ldg(a.xl + sel * d + k) : T(0);
     }
-    T lwy = T(0), wy = T(0);
-    if (a.lw) {
-        lwy = __ldg(a.lw + sel);
-        if (!STRICT && a.w) wy = __ldg(a.w + sel);
-    }
+    const YWeight<T> yw = load_yweight<T, STRICT>(a, sel);
     const long long rows = a.row_end - a.row_begin;
     const long long stride = (long long)gridDim.x * kThreads;
     const long long first = (long long)blockIdx.x * kThreads;
@@ -821,10 +841,10 @@ __global__ void __launch_bounds__(kThreads, 1) thin_step_chunked_pipe_kernel(Thi
                 double v;
                 const double av = a.A[li];
                 if constexpr (STRICT) {
-                    if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, lwy, wy), k);
+                    if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, yw), k);
                     v = __dadd_rn(av, __dmul_rn(2.0, k));
                 } else {
-                    v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, lwy, wy), k, av) : fma(2.0, k, av);
+                    v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, yw), k, av) : fma(2.0, k, av);
                 }
                 a.A[li] = v;
                 if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
@@ -846,7 +866,8 @@ __global__ void __launch_bounds__(kThreads, 1) thin_step_chunked_pipe_kernel(Thi
 constexpr int kPersistThreads = 512;
 constexpr int kPollPerLane = 5;                       // persistent grid <= 160 CTAs (one per SM)
 
-template <typename T, int D, bool STRICT, bool MULTI>
+// WDD (strict mode only): gradient-free weights from the per-row double-double exponentials in a.w (exp_sum_dd)
+template <typename T, int D, bool STRICT, bool MULTI, bool WDD>
 __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double sv[32];
@@ -900,7 +921,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                     k0 *= (double)(wi * wi);
                 } else {
                     lw_sh[slot] = lwi;
-                    const double wgt = exp((double)lwi + (double)lwi);
+                    double wgt;
+                    if constexpr (WDD) {
+                        const double2 e = __ldg(reinterpret_cast<const double2*>(a.w) + i);
+                        wgt = exp_sum_dd((double)lwi, (double)lwi, e.x, e.y, e.x, e.y);
+                    } else {
+                        wgt = exp((double)lwi + (double)lwi);
+                    }
                     k0 = STRICT ? __dmul_rn(wgt, k0) : wgt * k0;
                 }
             }
@@ -1012,6 +1039,14 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         load_row<D>(a.s, sel, sy);
         T lwy = T(0);
         if (a.lw) lwy = use_w ? __ldg(a.w + sel) : __ldg(a.lw + sel);
+        double ehy = 0.0, ely = 0.0;
+        if constexpr (WDD) {
+            if (a.lw) {
+                const double2 e = __ldg(reinterpret_cast<const double2*>(a.w) + sel);
+                ehy = e.x;
+                ely = e.y;
+            }
+        }
         bv = __longlong_as_double(0x7ff0000000000000LL);
         bi = 0xffffffffu;
         GFK_STAMP(step + 1, 0);
@@ -1029,13 +1064,22 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                     load_row<D>(a.x, i, xr);
                     load_row<D>(a.s, i, sr);
                 }
+                double2 ei = make_double2(0.0, 0.0);
+                if constexpr (WDD) {
+                    if (a.lw) ei = __ldg(reinterpret_cast<const double2*>(a.w) + i);   // in flight under the pair kernel
+                }
                 double k;
                 if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
                 else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
                 double v;
                 const double av = A_sh[slot];
                 if constexpr (STRICT) {
-                    if (a.lw) k = __dmul_rn(exp((double)lw_sh[slot] + (double)lwy), k);
+                    if (a.lw) {
+                        double wgt;
+                        if constexpr (WDD) wgt = exp_sum_dd((double)lw_sh[slot], (double)lwy, ei.x, ei.y, ehy, ely);
+                        else wgt = exp((double)lw_sh[slot] + (double)lwy);
+                        k = __dmul_rn(wgt, k);
+                    }
                     v = __dadd_rn(av, __dmul_rn(2.0, k));
                 } else {
                     if (a.lw) {
@@ -1156,6 +1200,19 @@ static cudaError_t launch_cooperative(void (*kernel)(KArgs...), unsigned grid, i
 #endif
 }
 
+// one instantiation of the single-launch kernel: opt-in shared memory, reset, cooperative launch
+template <typename T, int D, bool STRICT, bool MULTI, bool WDD>
+static int persistent_go(const ThinArgs<T>& a, const MailArgs& mail, int m, int rpt, int rpt_res, unsigned grid,
+                         int threads, size_t smem, cudaStream_t st) {
+    cudaError_t e = persistent_prepare(thin_persistent_kernel<T, D, STRICT, MULTI, WDD>, threads, smem);
+    if (e != cudaSuccess) return 0;
+    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail);
+    e = launch_cooperative(thin_persistent_kernel<T, D, STRICT, MULTI, WDD>, grid, threads, smem, st, a, m, rpt, rpt_res);
+    if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
+    count_launches(2);
+    return 1;
+}
+
 // persistent path: returns 1 if it ran, 0 if not eligible, < 0 on error
 template <typename T, int D, bool STRICT>
 static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, cudaStream_t st) {
@@ -1183,17 +1240,17 @@ static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, c
     const char* env = getenv("GFK_RESIDENT");
     if (env && env[0] == '0') rpt_res = 0;
     const size_t smem = base + (size_t)rpt_res * per_row_slot;
-    const bool multi = a.n_ranks > 1;
-    cudaError_t e = multi ? persistent_prepare(thin_persistent_kernel<T, D, STRICT, true>, threads, smem)
-                          : persistent_prepare(thin_persistent_kernel<T, D, STRICT, false>, threads, smem);
-    if (e != cudaSuccess) return 0;
-    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail);
-    e = multi ? launch_cooperative(thin_persistent_kernel<T, D, STRICT, true>, (unsigned)grid, threads, smem, st, a, m, rpt, rpt_res)
-              : launch_cooperative(thin_persistent_kernel<T, D, STRICT, false>, (unsigned)grid, threads, smem, st, a, m, rpt, rpt_res);
-    if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
-    count_launches(2);
-    return 1;
+    const unsigned g = (unsigned)grid;
+    if constexpr (STRICT) {
+        if (a.lw && a.w) {       // double-double exponentials present: weights without the device exp
+            return a.n_ranks > 1 ? persistent_go<T, D, STRICT, true, true>(a, mail, m, rpt, rpt_res, g, threads, smem, st)
+                                 : persistent_go<T, D, STRICT, false, true>(a, mail, m, rpt, rpt_res, g, threads, smem, st);
+        }
+    }
+    return a.n_ranks > 1 ? persistent_go<T, D, STRICT, true, false>(a, mail, m, rpt, rpt_res, g, threads, smem, st)
+                         : persistent_go<T, D, STRICT, false, false>(a, mail, m, rpt, rpt_res, g, threads, smem, st);
 }
+
 
 template <typename T, bool STRICT>
 static int try_persistent(const ThinArgs<T>& a, const MailArgs& mail, int d, int m, cudaStream_t st) {

@@ -56,7 +56,11 @@ typedef struct gfk_problem {
     const void* x;
     const void* s;
     const void* lw;   /* log-weights log q - log p (n), or NULL                             */
-    const void* w;    /* optional exp(lw) (n) for the fast modes; NULL: exp(lw_i + lw_j) per pair */
+    const void* w;    /* optional pre-exponentiated weights; NULL: exp(lw_i + lw_j) per pair with the device exp.
+                         Fast modes: exp(lw) (n).  GFK_F64_STRICT: double-double exp(lw) as (hi, lo) pairs (2n
+                         doubles, 16-byte aligned, gfk_exp_weights_dd) - the pair weight exp(fl(lw_i + lw_j)) is then
+                         formed with 12 IEEE operations, correctly rounded in all but ~2^-30 of the cases and
+                         identical on any machine; requires every |lw| <= 350 (gfk_log_weights_range)          */
     const void* xl;   /* optional x @ L (n, d) for a dense symmetric Gamma^-1 = L, or NULL       */
     int64_t n;        /* rows in x / s / lw (the full replica)                          */
     int32_t d;        /* columns                                                        */
@@ -110,9 +114,13 @@ size_t gfk_log_weights_ws_bytes(void);
 int gfk_log_weights(const double* log_p, const double* log_q, int64_t n, int use_cap, double range_cap,
                     double* lw, double* spread_host, void* ws, void* stream);
 int gfk_exp_weights(const void* lw, void* w, int64_t count, int is_f32, void* stream);
+/* Strict mode: ew[2i], ew[2i+1] = (hi, lo) with hi + lo = exp(lw_i) to ~2^-96 (double-double arithmetic, IEEE
+ * operations only).  ew: 2 * count doubles, 16-byte aligned.  Entries with |lw| > 350 are NaN markers: pass the
+ * array as gfk_problem.w only when gfk_log_weights_range shows every |lw| <= 350.  Asynchronous. */
+int gfk_exp_weights_dd(const double* lw, double* ew, int64_t count, void* stream);
 /* min and max of a log-weight vector (host out, 2 doubles).  SYNCHRONOUS.  The KSD row sums may use the
- * pre-exponentiated weights w = exp(lw) (one multiplication per pair instead of one exp) whenever every |lw| is far
- * from the overflow / underflow range of exp; the caller decides with this.  ws: gfk_log_weights_ws_bytes(). */
+ * pre-exponentiated weights (one multiplication per pair instead of one exp) whenever every |lw| is far from the
+ * overflow / underflow range of exp; the caller decides with this.  ws: gfk_log_weights_ws_bytes(). */
 int gfk_log_weights_range(const double* lw, int64_t n, double* min_max_host, void* ws, void* stream);
 
 /* ---- next: the Gaussian proxy of gaussian_thin, code/src/thinning.py:15-16 ----------------

@@ -39,6 +39,20 @@ void host_strict_powers(const double* q, int64_t n, double* p05, double* p15, do
     for (int64_t i = 0; i < n; ++i) gfk::strict_powers(q[i], p05[i], p15[i], p25[i]);
 }
 
+void host_exp_dd(const double* l, int64_t n, double* hi, double* lo) {
+    for (int64_t i = 0; i < n; ++i) gfk::exp_dd(l[i], hi[i], lo[i]);
+}
+
+// out[i] = exp(fl(a_i + b_i)) through the double-double route the strict kernels take
+void host_exp_sum_dd(const double* a, const double* b, int64_t n, double* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        double ah, al, bh, bl;
+        gfk::exp_dd(a[i], ah, al);
+        gfk::exp_dd(b[i], bh, bl);
+        out[i] = gfk::exp_sum_dd(a[i], b[i], ah, al, bh, bl);
+    }
+}
+
 void host_pairwise_dot(const double* a, const double* b, int64_t n, int d, double* out) {
     for (int64_t i = 0; i < n; ++i) {
         RowView av{a + i * d}, bv{b + i * d};

@@ -169,6 +169,14 @@ class SimProblem:
         if klw is not None and self.mode != F64_STRICT:
             self.w = guarded(klw.shape, klw.dtype)
             check(lib.gfk_exp_weights(ptr(klw), ptr(self.w), n, int(self.mode == F32_FAST), None))
+        elif klw is not None:                  # strict mode: double-double exponentials when the range allows
+            rng = (ctypes.c_double * 2)()
+            rws = guarded((lib.gfk_log_weights_ws_bytes(),), np.uint8)
+            check(lib.gfk_log_weights_range(ptr(klw), n, rng, ptr(rws), None))
+            self.lw_range = (rng[0], rng[1])
+            if -350.0 <= rng[0] and rng[1] <= 350.0 and os.environ.get('GFK_TEST_NO_EXP_DD') != '1':
+                self.w = guarded((n, 2), np.float64, fill=np.nan)
+                check(lib.gfk_exp_weights_dd(ptr(klw), ptr(self.w), n, None))
         self._keep = (kx, ks, klw, kxl)
         self.struct = Problem(x=kx.ctypes.data, s=ks.ctypes.data, lw=klw.ctypes.data if klw is not None else None,
                               w=self.w.ctypes.data if self.w is not None else None,
@@ -195,31 +203,12 @@ class SimProblem:
     def _sel(self, sel):
         return None if sel is None else dev(np.asarray(sel), np.uint32)
 
-    def _ksd_struct(self):
-        """Mirror of _engine.SteinProblem._ksd_struct: pre-exponentiated weights for the KSD row sums when safe."""
-        if self.lw is None or self.w is not None:
-            return self.struct
-        if getattr(self, '_struct_ksd', None) is None:
-            lib = load()
-            rng = (ctypes.c_double * 2)()
-            ws = guarded((lib.gfk_log_weights_ws_bytes(),), np.uint8)
-            check(lib.gfk_log_weights_range(ptr(self.lw), self.n, rng, ptr(ws), None))
-            self.lw_range = (rng[0], rng[1])
-            if -300.0 <= rng[0] and rng[1] <= 300.0:
-                self._w_ksd = guarded(self.lw.shape, np.float64)
-                check(lib.gfk_exp_weights(ptr(self.lw), ptr(self._w_ksd), self.n, 0, None))
-                self._struct_ksd = Problem.from_buffer_copy(self.struct)
-                self._struct_ksd.w = self._w_ksd.ctypes.data
-            else:
-                self._struct_ksd = self.struct
-        return self._struct_ksd
-
     def ksd_rowsums(self, sel=None, m=None, part=0, n_parts=1):
         lib = load()
         sel_dev = self._sel(sel)
         m = int(m if m is not None else (len(sel) if sel is not None else self.n))
         low, diag = guarded((m,), np.float64, fill=np.nan), guarded((m,), np.float64, fill=np.nan)
-        check(lib.gfk_ksd_rowsums(ctypes.byref(self._ksd_struct()), ptr(sel_dev), m, part, n_parts, ptr(low), ptr(diag), None))
+        check(lib.gfk_ksd_rowsums(ctypes.byref(self.struct), ptr(sel_dev), m, part, n_parts, ptr(low), ptr(diag), None))
         return low.copy(), diag.copy()
 
     def ksd(self, sel=None, m=None, n_parts=1):

@@ -438,12 +438,14 @@ def test_multi_rank_thinning_and_ksd(world, tmp_path):
         assert p.returncode == 0 and 'SIMT_RANK_OK %d %d' % (r, world) in out, out[-3000:]
 
 
-def test_ksd_weights_preexponentiated_only_when_safe():
-    """Strict-mode KSD multiplies by w_i w_j = exp(lw_i) exp(lw_j) (gfk_log_weights_range says when that is safe) and
-    falls back to exp(lw_i + lw_j) per pair when a log-weight is extreme - both within 1e-10 of the oracle."""
+def test_strict_weights_double_double_when_safe_device_exp_otherwise(monkeypatch):
+    """Strict mode forms exp(fl(lw_i + lw_j)) from per-row double-double exponentials (gfk_exp_weights_dd, 12 IEEE
+    operations per pair) when gfk_log_weights_range shows every |lw| <= 350, and keeps exp() per pair otherwise.
+    Both must select the oracle's indices; pair values agree with the oracle to the last bit wherever numpy's own
+    exp and pow are correctly rounded."""
     rng = np.random.default_rng(81)
-    n = 200
-    x, g = _mcmc_like(rng, n, 3, dup=0.0)
+    n = 600
+    x, g = _mcmc_like(rng, n, 3, dup=0.3)
     log_p = -0.5 * np.sum(x ** 2, axis=1)
     for shift, safe in ((0.0, True), (650.0, False)):
         log_q = log_p + np.sin(x[:, 0])
@@ -451,20 +453,54 @@ def test_ksd_weights_preexponentiated_only_when_safe():
         log_q[1::2] -= shift
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
-            ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med')
-        p = H.SimProblem(x, g, log_p, log_q, preconditioner='med')
-        low, diag = p.ksd_rowsums()
+            ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, standardize=False)
+        p = H.SimProblem(x, g, log_p, log_q, standardize=False)
         assert np.allclose(p.lw_range, (np.min(log_q - log_p), np.max(log_q - log_p)), rtol=0, atol=0)
-        assert (p._struct_ksd.w is not None) == safe
+        assert (p.w is not None) == safe
+        ia, ib = rng.integers(0, n, 3000), rng.integers(0, n, 3000)
+        if not safe:
+            ia, ib = 2 * (ia // 2), 2 * (ib // 2) + 1                    # (+650, -650) pairs: finite weights
         with np.errstate(over='ignore', invalid='ignore'):
-            km = os_.kmat(ref, n)
+            want = ref(ia, ib)
+        got = p.pairs(ia, ib)
+        np.testing.assert_allclose(got, want, rtol=1e-14)
         if safe:
+            assert np.mean(got == want) > 0.85
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                expect = ot.thin_gf(x, log_p, log_q, g, 30, standardize=False)
+            for env in STRATEGIES.values():
+                for k in ('GFK_PERSISTENT', 'GFK_RESIDENT'):
+                    monkeypatch.delenv(k, raising=False)
+                for k, v in env.items():
+                    monkeypatch.setenv(k, v)
+                assert np.array_equal(p.thin(30)[0], expect)
             np.testing.assert_allclose(p.ksd(), os_.ksd(ref, n), rtol=1e-10)
-        else:
-            # row sums mix magnitudes e^+-1300; compare the finite, well-scaled entries pair by pair instead
-            ia, ib = np.arange(0, n, 2), np.arange(1, n, 2)
-            np.testing.assert_allclose(p.pairs(ia, ib), km[ia, ib], rtol=1e-10)
-            assert np.all(np.isfinite(low[1::2]) | np.isinf(low[1::2]))
+    # the device-exp route (forced) and the double-double route agree to 1 ulp per weight and select the same points
+    log_q = log_p + np.sin(x[:, 0])
+    a = H.SimProblem(x, g, log_p, log_q, preconditioner='med')
+    monkeypatch.setenv('GFK_TEST_NO_EXP_DD', '1')
+    b = H.SimProblem(x, g, log_p, log_q, preconditioner='med')
+    assert a.w is not None and b.w is None
+    assert np.array_equal(a.thin(25)[0], b.thin(25)[0])
+    ia, ib = rng.integers(0, n, 2000), rng.integers(0, n, 2000)
+    np.testing.assert_allclose(a.pairs(ia, ib), b.pairs(ia, ib), rtol=4e-16)
+
+
+def test_double_double_exponentials_are_accurate_to_2_pow_minus_90():
+    import ctypes
+    from decimal import Decimal, getcontext
+    lib = H.load()
+    rng = np.random.default_rng(5)
+    l = np.concatenate([rng.uniform(-350, 350, 600), rng.uniform(-3, 3, 400), [0.0, 350.0, -350.0, 400.0]])
+    ld, ew = H.dev(l), H.guarded((l.size, 2), np.float64, fill=0.0)
+    H.check(lib.gfk_exp_weights_dd(H.ptr(ld), H.ptr(ew), l.size, None))
+    assert np.all(np.isnan(ew[-1]))                                      # beyond the limit: NaN marker, never used
+    getcontext().prec = 60
+    for v, (hi, lo) in zip(l[:-1], ew[:-1]):
+        t = Decimal(float(v)).exp()
+        assert abs((Decimal(float(hi)) + Decimal(float(lo)) - t) / t) < Decimal(2) ** -90
+        assert float(hi) == float(t)                                     # the high part alone is the correctly rounded exp
 
 
 # ---- edge sizes and BASELINE-shaped inputs -----------------------------------------------------------------------
