@@ -90,6 +90,16 @@ GFK_HD unsigned exponent_field(double v) {
 }
 // |v| within [2^-span, 2^span]
 GFK_HD bool exponent_within(double v, unsigned span) { return (exponent_field(v) - (0x3ffu - span)) <= 2u * span; }
+// v == +-0, on the integer pipe
+GFK_HD bool is_zero(double v) {
+#if defined(__CUDA_ARCH__)
+    return (((unsigned)__double2hiint(v) & 0x7fffffffu) | (unsigned)__double2loint(v)) == 0u;
+#else
+    unsigned long long bits;
+    memcpy(&bits, &v, sizeof(bits));
+    return (bits << 1) == 0ull;
+#endif
+}
 
 // Correctly rounded quotient n / p from an approximate reciprocal rinv ~ 1/p (a few ulp): one
 // Markstein correction step.  q0 = n * rinv is within a few ulp of n / p, the residual n - q0 * p is
@@ -223,8 +233,8 @@ GFK_HD double strict_finish(double s1, double s2, double s3, double s4, const KP
     const double n2 = nf_add(kp.trace, s3);
     const double n3 = s4;
     // one exponent test per pair instead of guards around every operation
-    const bool regular = exponent_within(qf, 150u) && (exponent_within(n1, 400u) || n1 == 0.0) &&
-                         (exponent_within(n2, 400u) || n2 == 0.0) && (exponent_within(n3, 400u) || n3 == 0.0);
+    const bool regular = exponent_within(qf, 150u) && (exponent_within(n1, 400u) || is_zero(n1)) &&
+                         (exponent_within(n2, 400u) || is_zero(n2)) && (exponent_within(n3, 400u) || is_zero(n3));
     if (regular) {
         double p05, p15, p25, r05, r15, r25;
         strict_powers_r(qf, p05, p15, p25, r05, r15, r25);
@@ -392,6 +402,12 @@ struct Cand {
     double v;
     unsigned long long i;
 };
+
+// the same decision for a scan in INCREASING index order (a tie keeps the earlier row, the first NaN sticks):
+// `none` = nothing taken yet.  Two floating-point compares instead of five.
+GFK_HD bool cand_better_in_order(double v, double best, bool none) {
+    return none || ((best == best) && !(v >= best));
+}
 
 GFK_HD bool cand_better(double va, unsigned long long ia, double vb, unsigned long long ib) {
     const bool na = (va != va), nb = (vb != vb);

@@ -932,7 +932,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 }
             }
             A_sh[slot] = k0;
-            if (cand_better(k0, (unsigned)i, bv, bi)) { bv = k0; bi = (unsigned)i; }
+            if (cand_better_in_order(k0, bv, bi == 0xffffffffu)) { bv = k0; bi = (unsigned)i; }   // rows in increasing order
         }
     }
 
@@ -1090,7 +1090,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                     }
                 }
                 A_sh[slot] = v;
-                if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
+                if (cand_better_in_order(v, bv, bi == 0xffffffffu)) { bv = v; bi = (unsigned)i; }
             }
         }
     }

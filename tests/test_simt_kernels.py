@@ -199,6 +199,25 @@ def test_nan_objective_is_selected_first_like_numpy(monkeypatch):
         assert np.array_equal(idx, expect)
 
 
+def test_infinite_objectives_like_numpy(monkeypatch):
+    """All objectives +inf: np.argmin returns index 0 every step; some +inf: they never win."""
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((700, 2))
+    g_all = np.full((700, 2), 1e200)
+    g_some = g_all.copy()
+    g_some[300:] = rng.standard_normal((400, 2))
+    for g in (g_all, g_some):
+        with np.errstate(all='ignore'):
+            expect = ot.thin(x, g, 4, standardize=False)
+        for env in STRATEGIES.values():
+            for k in ('GFK_PERSISTENT', 'GFK_RESIDENT'):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            for precision in ('f64', 'f64-fast'):
+                assert np.array_equal(H.SimProblem(x, g, standardize=False, precision=precision).thin(4)[0], expect)
+
+
 # ---- kernel values, Gram matrix, KSD ---------------------------------------------------------------------------
 @pytest.mark.parametrize('gf', [False, True])
 @pytest.mark.parametrize('d', [1, 2, 7, 10, 33, 70])
