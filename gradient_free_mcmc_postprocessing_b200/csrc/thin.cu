@@ -885,6 +885,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     // waits for the slowest CTA).  Its rows are dealt round-robin over the CTAs instead, so all SMs carry the same load.
     const long long last_base = (long long)(rpt - 1) * TT;
     const long long last_e = (long long)tid * gridDim.x + blockIdx.x;
+    const long long i_last = a.row_begin + last_base + last_e;     // this thread's global row of the last pass
     const int slots = rpt * nthr;
     double* A_sh = reinterpret_cast<double*>(psm);
     T* lw_sh = reinterpret_cast<T*>(A_sh + slots);              // lw (strict / no w) or w (fast)
@@ -1050,47 +1051,59 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         bv = __longlong_as_double(0x7ff0000000000000LL);
         bi = 0xffffffffu;
         GFK_STAMP(step + 1, 0);
+        // one row of the update: kernel value against y, weight, running objective, in-order argmin
+        auto update_row = [&](long long i, int slot, const T (&xr)[D], const T (&sr)[D]) {
+            double2 ei = make_double2(0.0, 0.0);
+            if constexpr (WDD) {
+                if (a.lw) ei = __ldg(reinterpret_cast<const double2*>(a.w) + i);   // in flight under the pair kernel
+            }
+            double k;
+            if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
+            else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
+            double v;
+            const double av = A_sh[slot];
+            if constexpr (STRICT) {
+                if (a.lw) {
+                    double wgt;
+                    if constexpr (WDD) wgt = exp_sum_dd((double)lw_sh[slot], (double)lwy, ei.x, ei.y, ehy, ely);
+                    else wgt = exp((double)lw_sh[slot] + (double)lwy);
+                    k = __dmul_rn(wgt, k);
+                }
+                v = __dadd_rn(av, __dmul_rn(2.0, k));
+            } else {
+                if (a.lw) {
+                    const double wgt = use_w ? (double)(lw_sh[slot] * lwy) : exp((double)lw_sh[slot] + (double)lwy);
+                    v = fma(2.0 * wgt, k, av);
+                } else {
+                    v = fma(2.0, k, av);
+                }
+            }
+            A_sh[slot] = v;
+            if (cand_better_in_order(v, bv, bi == 0xffffffffu)) { bv = v; bi = (unsigned)i; }
+        };
+        // Two loops so that neither carries the other's address arithmetic: rows resident in shared memory first,
+        // then the rows streamed through L2.  The global row index advances by TT per pass; the last pass uses the
+        // round-robin dealing (i_last).  Rows are visited in increasing index order (cand_better_in_order).
+        long long i_cur = a.row_begin + gt;
+        int slot = tid;
 #pragma unroll 2
-        for (int j = 0; j < rpt; ++j) {
-            const long long li = (j == rpt - 1) ? last_base + last_e : (long long)j * TT + gt;
-            const int slot = j * nthr + tid;
-            if (li < rows) {
-                const long long i = a.row_begin + li;
+        for (int j = 0; j < rpt_res; ++j, i_cur += TT, slot += nthr) {
+            const long long i = (j == rpt - 1) ? i_last : i_cur;
+            if (i < a.row_end) {
                 T xr[D], sr[D];
-                if (j < rpt_res) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots_res + slot]; sr[k] = ss[k * slots_res + slot]; }
-                } else {
-                    load_row<D>(a.x, i, xr);
-                    load_row<D>(a.s, i, sr);
-                }
-                double2 ei = make_double2(0.0, 0.0);
-                if constexpr (WDD) {
-                    if (a.lw) ei = __ldg(reinterpret_cast<const double2*>(a.w) + i);   // in flight under the pair kernel
-                }
-                double k;
-                if constexpr (STRICT) k = pair_strict<D>(xr, y, sr, sy, a.kp);
-                else k = (double)pair_fast<T, D, false>(xr, y, sr, sy, xr, y, a.kp);
-                double v;
-                const double av = A_sh[slot];
-                if constexpr (STRICT) {
-                    if (a.lw) {
-                        double wgt;
-                        if constexpr (WDD) wgt = exp_sum_dd((double)lw_sh[slot], (double)lwy, ei.x, ei.y, ehy, ely);
-                        else wgt = exp((double)lw_sh[slot] + (double)lwy);
-                        k = __dmul_rn(wgt, k);
-                    }
-                    v = __dadd_rn(av, __dmul_rn(2.0, k));
-                } else {
-                    if (a.lw) {
-                        const double wgt = use_w ? (double)(lw_sh[slot] * lwy) : exp((double)lw_sh[slot] + (double)lwy);
-                        v = fma(2.0 * wgt, k, av);
-                    } else {
-                        v = fma(2.0, k, av);
-                    }
-                }
-                A_sh[slot] = v;
-                if (cand_better_in_order(v, bv, bi == 0xffffffffu)) { bv = v; bi = (unsigned)i; }
+                for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots_res + slot]; sr[k] = ss[k * slots_res + slot]; }
+                update_row(i, slot, xr, sr);
+            }
+        }
+#pragma unroll 2
+        for (int j = rpt_res; j < rpt; ++j, i_cur += TT, slot += nthr) {
+            const long long i = (j == rpt - 1) ? i_last : i_cur;
+            if (i < a.row_end) {
+                T xr[D], sr[D];
+                load_row<D>(a.x, i, xr);
+                load_row<D>(a.s, i, sr);
+                update_row(i, slot, xr, sr);
             }
         }
     }
