@@ -597,17 +597,17 @@ def test_warp_specialised_ksd_kernel_equals_the_tile_kernel(d, monkeypatch):
     np.testing.assert_allclose(H.SimProblem(x, g, log_p, log_q, preconditioner='med').ksd(), os_.ksd(ref, n), rtol=1e-10)
 
 
-@pytest.mark.parametrize('d', [5, 8, 9, 16, 17, 33, 64, 100])
+@pytest.mark.parametrize('d', [5, 9, 17, 64])
 def test_pipelined_step_kernel_equals_the_slab_kernel(d, monkeypatch):
     """GFK_CHUNK_PIPE=1: thin_step_chunked_pipe_kernel (three slabs in flight per CTA) must select the oracle's indices
     and leave bit-identical objectives to thin_step_chunked_kernel, in every precision, under any thread schedule."""
     monkeypatch.setenv('GFK_PERSISTENT', '0')
     monkeypatch.setenv('SIMT_SMS', '2')                          # 2 CTAs x 256 rows: several tiles per CTA
     rng = np.random.default_rng(9000 + d)
-    x, g = _mcmc_like(rng, 1333, d)
+    x, g = _mcmc_like(rng, 1100, d)
     log_p = -0.5 * np.sum(x ** 2, axis=1) / d
     log_q = log_p + 0.5 * np.sin(x[:, 0])
-    m = 9
+    m = 6
     expect = ot.thin_gf(x, log_p, log_q, g, m, preconditioner='med')
     for precision in ('f64', 'f64-fast', 'f32'):
         monkeypatch.delenv('GFK_CHUNK_PIPE', raising=False)
