@@ -51,6 +51,7 @@ def parse_args():
                     choices=['f64', 'f64-fast', 'f32'])
     ap.add_argument('--cpu-baseline-m', type=int, default=40)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the secondary C4 KSD measurement')
     return ap.parse_args()
 
 
@@ -180,6 +181,37 @@ class ClockSampler(threading.Thread):
             return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
         return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
                 'samples': len(self.samples)}
+
+
+def measure_ksd_c4(dev, fp64_peak_tflops):
+    """Secondary number (not the headline `value`): BASELINE config C4, the full O(n^2) gradient-free KSD of
+    n = 2 x 10^5, d = 10 samples with the median-heuristic preconditioner; pair-evals = n (n + 1) / 2."""
+    import torch
+    from gradient_free_mcmc_postprocessing_b200 import synthetic
+    from gradient_free_mcmc_postprocessing_b200._engine import SteinProblem
+    try:
+        n, d = 200_000, 10
+        c = synthetic.config_c4(n=n, d=d)
+        inputs = {k: torch.from_numpy(np.ascontiguousarray(c[k])).to(dev) for k in ('sample', 'gradient_q', 'log_p', 'log_q')}
+        prob = SteinProblem(inputs['sample'], inputs['gradient_q'], log_p=inputs['log_p'], log_q=inputs['log_q'],
+                            preconditioner='med', precision='f64', device=dev)
+        prob.ksd(None, 20_000)                                  # warm-up
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ks = prob.ksd(None, n)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3
+        pairs = n * (n + 1) / 2
+        flops = 8 * d + 16 + 3
+        return {'workload': f'C4 full gradient-free KSD n={n} d={d} med, f64', 'seconds': sec,
+                'pair_evals_per_s': pairs / sec, 'ksd': float(ks[-1]),
+                'roofline': {'bound': 'fp64', 'achieved': pairs * flops / sec / 1e12, 'peak': fp64_peak_tflops,
+                             'unit': 'TFLOP/s', 'frac': pairs * flops / sec / 1e12 / fp64_peak_tflops,
+                             'flops_per_pair': flops, 'peak_source': 'measured (gfk_fma_peak)'}}
+    except Exception as e:   # noqa: BLE001 - a secondary number must not take the headline line down with it
+        return {'error': repr(e)[:300]}
 
 
 # ---- our arm ----------------------------------------------------------------------------------------------
@@ -345,6 +377,8 @@ def run_ours(args):
             sm = strong['dev_ms'] / max(2, args.steps // 2)
             line['strong'] = {'n': N_PER_GPU, 'ms_per_step': sm, 'value': N_PER_GPU * M / (sm * 1e-3),
                               'e2e_ms_per_step': strong['e2e_ms'] / max(2, args.steps // 2)}
+        if world == 1 and not args.no_secondary:
+            line['ksd_c4'] = measure_ksd_c4(dev, fp64.value)
         if world == 1 and not args.no_cpu_baseline:
             m_cpu = args.cpu_baseline_m
             v, dt = cpu_oracle_throughput(res['host_np'], m_cpu, 1)

@@ -21,10 +21,10 @@ if [ -f libgfk_trace.so ]; then
 fi
 echo "== ncu launch list of the bench"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/bench_launches_ncu.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "rc=$?"
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/ncu_launches.log 2>&1; echo "rc=$?"
 echo "== ncu --set full: persistent thinning kernel, KSD row sums, d=64 step kernel, KDE, energy"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:thin_persistent -c 1 -o gpurun_out/prof_thin_persistent -f \
-    python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_thin.log 2>&1; echo "rc=$?"
+    python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-secondary > gpurun_out/ncu_thin.log 2>&1; echo "rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:ksd_rowsum -c 2 -o gpurun_out/prof_ksd_rowsum -f \
     python tools/ncu_targets.py ksd > gpurun_out/ncu_ksd.log 2>&1; echo "rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:thin_step_chunked -s 5 -c 1 -o gpurun_out/prof_thin_chunked -f \
