@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument('--cpu-baseline-m', type=int, default=40)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the secondary C4 KSD measurement')
+    ap.add_argument('--secondary-only', type=float, default=None, metavar='FP64_PEAK_TFLOPS',
+                    help='(internal) run only the secondary C4 KSD measurement and print its JSON object')
     return ap.parse_args()
 
 
@@ -211,6 +213,21 @@ def measure_ksd_c4(dev, fp64_peak_tflops):
                              'unit': 'TFLOP/s', 'frac': pairs * flops / sec / 1e12 / fp64_peak_tflops,
                              'flops_per_pair': flops, 'peak_source': 'measured (gfk_fma_peak)'}}
     except Exception as e:   # noqa: BLE001 - a secondary number must not take the headline line down with it
+        return {'error': repr(e)[:300]}
+
+
+def secondary_in_subprocess(fp64_peak_tflops, timeout_s=240):
+    """The secondary measurement runs in its own process: whatever happens there (a CUDA error, a hang) cannot take
+    the headline measurement - already complete at this point - down with it."""
+    import subprocess
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--secondary-only', repr(float(fp64_peak_tflops))],
+                             capture_output=True, text=True, timeout=timeout_s)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)
+        return {'error': ('no output; rc=%d; ' % out.returncode) + out.stderr[-300:]}
+    except Exception as e:   # noqa: BLE001
         return {'error': repr(e)[:300]}
 
 
@@ -378,7 +395,7 @@ def run_ours(args):
             line['strong'] = {'n': N_PER_GPU, 'ms_per_step': sm, 'value': N_PER_GPU * M / (sm * 1e-3),
                               'e2e_ms_per_step': strong['e2e_ms'] / max(2, args.steps // 2)}
         if world == 1 and not args.no_secondary:
-            line['ksd_c4'] = measure_ksd_c4(dev, fp64.value)
+            line['ksd_c4'] = secondary_in_subprocess(fp64.value)
         if world == 1 and not args.no_cpu_baseline:
             m_cpu = args.cpu_baseline_m
             v, dt = cpu_oracle_throughput(res['host_np'], m_cpu, 1)
@@ -399,6 +416,12 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    if args.secondary_only is not None:
+        import torch
+        warnings.simplefilter('ignore')
+        torch.cuda.set_device(0)
+        print(json.dumps(measure_ksd_c4(torch.device('cuda', 0), args.secondary_only)), flush=True)
+        return
     if args.impl == 'reference':
         run_reference(args)
     else:
