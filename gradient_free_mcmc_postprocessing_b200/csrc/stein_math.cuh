@@ -133,13 +133,10 @@ GFK_HD void strict_powers_r(double q, double& p05, double& p15, double& p25, dou
     double l1 = nf_fma(q, s, -h1);                          // exact low part of q*s
     l1 = nf_fma(q, sl, l1);
     p15 = nf_add(h1, l1);
-    // q^2.5
-    const double qh = nf_mul(q, q);
-    const double ql = nf_fma(q, q, -qh);                    // exact low part of q*q
-    const double h2 = nf_mul(qh, s);
-    double l2 = nf_fma(qh, s, -h2);
-    l2 = nf_fma(qh, sl, l2);
-    l2 = nf_fma(ql, s, l2);
+    // q^2.5 = q * (h1 + l1): the double-double q^1.5 times q, rounded once
+    const double h2 = nf_mul(q, h1);
+    double l2 = nf_fma(q, h1, -h2);                         // exact low part of q*h1
+    l2 = nf_fma(q, l1, l2);
     p25 = nf_add(h2, l2);
     const double r2 = nf_mul(r, r);
     r05 = r;
