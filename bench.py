@@ -216,6 +216,33 @@ def measure_ksd_c4(dev, fp64_peak_tflops):
         return {'error': repr(e)[:300]}
 
 
+def measure_thin_c2(dev):
+    """Secondary number: BASELINE config C2 (Lotka-Volterra-shaped chain, d = 4, n = 2 x 10^5, m = 1000, score-based
+    kernel, 'med'; runs of duplicated rows) - the whole job from device-resident inputs, best of 3."""
+    import torch
+    from gradient_free_mcmc_postprocessing_b200 import synthetic
+    from gradient_free_mcmc_postprocessing_b200._engine import SteinProblem
+    try:
+        c = synthetic.config_c2()
+        x = torch.from_numpy(np.ascontiguousarray(c['sample'])).to(dev)
+        g = torch.from_numpy(np.ascontiguousarray(c['gradient'])).to(dev)
+        n, m = x.shape[0], int(c['m'])
+        best, idx = 1e30, None
+        for rep in range(4):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            idx = SteinProblem(x, g, preconditioner='med', precision='f64', device=dev).thin(m)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep > 0:
+                best = min(best, e0.elapsed_time(e1) * 1e-3)
+        return {'workload': f'C2 score-based Stein thinning n={n} d=4 m={m} med, f64', 'seconds': best,
+                'pair_evals_per_s': n * m / best, 'unique_selected': int(len(np.unique(idx)))}
+    except Exception as e:   # noqa: BLE001
+        return {'error': repr(e)[:300]}
+
+
 def secondary_in_subprocess(fp64_peak_tflops, timeout_s=240):
     """The secondary measurement runs in its own process: whatever happens there (a CUDA error, a hang) cannot take
     the headline measurement - already complete at this point - down with it."""
@@ -226,9 +253,9 @@ def secondary_in_subprocess(fp64_peak_tflops, timeout_s=240):
         for ln in reversed(out.stdout.strip().splitlines()):
             if ln.startswith('{'):
                 return json.loads(ln)
-        return {'error': ('no output; rc=%d; ' % out.returncode) + out.stderr[-300:]}
+        return {'secondary_error': ('no output; rc=%d; ' % out.returncode) + out.stderr[-300:]}
     except Exception as e:   # noqa: BLE001
-        return {'error': repr(e)[:300]}
+        return {'secondary_error': repr(e)[:300]}
 
 
 # ---- our arm ----------------------------------------------------------------------------------------------
@@ -395,7 +422,7 @@ def run_ours(args):
             line['strong'] = {'n': N_PER_GPU, 'ms_per_step': sm, 'value': N_PER_GPU * M / (sm * 1e-3),
                               'e2e_ms_per_step': strong['e2e_ms'] / max(2, args.steps // 2)}
         if world == 1 and not args.no_secondary:
-            line['ksd_c4'] = secondary_in_subprocess(fp64.value)
+            line.update(secondary_in_subprocess(fp64.value))       # keys: ksd_c4, thin_c2 (or secondary_error)
         if world == 1 and not args.no_cpu_baseline:
             m_cpu = args.cpu_baseline_m
             v, dt = cpu_oracle_throughput(res['host_np'], m_cpu, 1)
@@ -420,7 +447,9 @@ def main():
         import torch
         warnings.simplefilter('ignore')
         torch.cuda.set_device(0)
-        print(json.dumps(measure_ksd_c4(torch.device('cuda', 0), args.secondary_only)), flush=True)
+        dev0 = torch.device('cuda', 0)
+        print(json.dumps({'thin_c2': measure_thin_c2(dev0), 'ksd_c4': measure_ksd_c4(dev0, args.secondary_only)}),
+              flush=True)
         return
     if args.impl == 'reference':
         run_reference(args)
