@@ -7,7 +7,10 @@
 One "step" is one complete thinning job (n candidates -> m selections): standardisation, median
 preconditioner, log-weights and the m-step greedy loop.  Workload at N = 1: BASELINE.json config C3
 (synthetic d=4 Gaussian mixture, n = 10^6, m = 1000, gradient-free kernel, 'med' preconditioner) -
-the configuration the north-star target is quoted on.  At N > 1 (one process per GPU, torchrun) the
+the configuration the north-star target is quoted on.  The proxy q is the same mixture with its covariances widened by
+1.3 (synthetic.config_c3): under the moment-matched Gaussian proxy gradient-free thinning degenerates at this n (the
+search returns the same one or two points), which would make the index-parity check vacuous; per-step arithmetic is
+identical for either proxy.  At N > 1 (one process per GPU, torchrun) the
 candidate rows are sharded across ranks and the ranks exchange one (value, index) pair per greedy
 step over NCCL; default scaling is weak (10^6 candidate rows per GPU), `--scaling strong` keeps
 n = 10^6 in total (the literal C3-on-8-GPUs case, also reported under "strong" in the weak line).
@@ -391,7 +394,7 @@ def run_ours(args):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64' if args.precision != 'f32' else 'f32',
             'data': 'synthetic',
-            'config': {'workload': f'C3 gradient-free Stein thinning: d={D} Gaussian mixture, n={n_total} '
+            'config': {'workload': f'C3 gradient-free Stein thinning: d={D} Gaussian mixture (proxy: same mixture, covariances x 1.3), n={n_total} '
                                    f'({rows_local} candidate rows per GPU), m={M}, preconditioner=med, '
                                    f'precision={args.precision}',
                        'thinning_wall_time_ms': ms_per_step, 'l2': 'flushed between timed steps (512 MiB write)',

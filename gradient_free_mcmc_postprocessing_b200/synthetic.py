@@ -97,13 +97,26 @@ def _random_mixture(d, k, rng, spread=2.0):
     return weights, means, np.array(covs)
 
 
-def config_c3(n=1_000_000, d=4, seed=12345, m=1000, k=3):
-    """C3: d=4 Gaussian mixture, GF thinning with a moment-matched Gaussian proxy, 'med'."""
+def config_c3(n=1_000_000, d=4, seed=12345, m=1000, k=3, proxy='wide-mixture', inflation=1.3):
+    """C3: d=4 Gaussian mixture, gradient-free thinning, 'med'.
+
+    proxy='wide-mixture' (default): q is the same mixture with every covariance inflated by `inflation` - a proxy
+    with heavier tails than the target, under which the selections are all distinct.  proxy='gaussian': the
+    moment-matched Gaussian of SURVEY.md section 8d; at n >= 10^5 it makes gradient-free thinning degenerate (the
+    log-weights spread over ~15 and the search keeps returning the same one or two points - the pathology the
+    reference shows for its Laplace proxy, Gaussian_mixture.ipynb#c110-#c111), so index parity on it says little.
+    The arithmetic per greedy step is the same for both."""
     rng = np.random.default_rng(seed)
     weights, means, covs = _random_mixture(d, k, rng, spread=1.0)
     rvs, logpdf, score = make_mvn_mixture(weights, means, covs)
     sample = rvs(n, rng)
-    log_q, gradient_q, _, _ = gaussian_proxy(sample)
+    if proxy == 'gaussian':
+        log_q, gradient_q, _, _ = gaussian_proxy(sample)
+    elif proxy == 'wide-mixture':
+        _, logpdf_q, score_q = make_mvn_mixture(weights, means, covs * inflation)
+        log_q, gradient_q = logpdf_q(sample), score_q(sample)
+    else:
+        raise ValueError("proxy must be 'wide-mixture' or 'gaussian'")
     return dict(kind='gf', sample=sample, log_p=logpdf(sample), log_q=log_q, gradient_q=gradient_q,
                 m=m, preconditioner='med')
 

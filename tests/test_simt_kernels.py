@@ -629,3 +629,21 @@ def test_pipelined_step_kernel_equals_the_slab_kernel(d, monkeypatch):
     monkeypatch.setenv('GFK_CHUNK_PIPE', '1')
     got = p.thin(4)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_full_size_c3_on_the_b200_grid_shape(monkeypatch):
+    """BASELINE config C3 at full size (n = 10^6, d = 4, gradient-free, 'med') with the launch geometry of a B200:
+    148 concurrently running CTAs of 512 threads, 14 rows per thread of which 3 stay in shared memory, every CTA
+    polling all 148 flag-in-data slots (5 per lane).  A prefix of the greedy search must equal the oracle's."""
+    from gradient_free_mcmc_postprocessing_b200 import synthetic
+    monkeypatch.setenv('SIMT_SMS', '148')
+    c = synthetic.config_c3()
+    m = 8
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        expect = ot.thin_gf(c['sample'], c['log_p'], c['log_q'], c['gradient_q'], m, preconditioner='med')
+    assert len(np.unique(expect)) == m                       # a healthy proxy: distinct selections
+    for precision in ('f64', 'f64-fast'):
+        p = H.SimProblem(c['sample'], c['gradient_q'], c['log_p'], c['log_q'], preconditioner='med', precision=precision)
+        idx, _ = p.thin(m)
+        assert np.array_equal(idx, expect), precision
