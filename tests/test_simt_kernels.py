@@ -643,6 +643,9 @@ def test_full_size_c3_on_the_b200_grid_shape(monkeypatch):
         warnings.simplefilter('ignore')
         expect = ot.thin_gf(c['sample'], c['log_p'], c['log_q'], c['gradient_q'], m, preconditioner='med')
     assert len(np.unique(expect)) == m                       # a healthy proxy: distinct selections
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'full_size_indices.npz'))
+    assert np.array_equal(golden['c3_idx'][:m], expect)      # the committed full-length sequence is the oracle's
+    assert np.array_equal(golden['c3_idx'], golden['c3_idx_kernels']) and np.array_equal(golden['c2_idx'], golden['c2_idx_kernels'])
     for precision in ('f64', 'f64-fast'):
         p = H.SimProblem(c['sample'], c['gradient_q'], c['log_p'], c['log_q'], preconditioner='med', precision=precision)
         idx, _ = p.thin(m)
