@@ -56,6 +56,11 @@ def load():
 
 
 def set_schedule(random=False, seed=1):
+    """Thread order between rendezvous points.  SIMT_FORCE_RANDOM=<seed> turns every test into a random-schedule
+    run (a one-off robustness sweep: `SIMT_FORCE_RANDOM=7 python -m pytest tests -m "not gpu" -k simt`)."""
+    forced = os.environ.get('SIMT_FORCE_RANDOM')
+    if forced:
+        random, seed = True, int(forced)
     load().simt_set_schedule(int(bool(random)), int(seed))
 
 
