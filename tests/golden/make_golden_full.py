@@ -1,4 +1,4 @@
-"""Full-length index sequences of BASELINE configs C2 and C3 from the numpy ORACLE (oracle/stein_thinning_oracle),
+"""Full-length index sequences of BASELINE configs C2, C3 and C5 from the numpy ORACLE (oracle/stein_thinning_oracle),
 for the `-m gpu` tests to compare all m selections with (the oracle needs minutes at these sizes, so it cannot run
 inside the tests).  Also runs the emulator build of the kernels on the same inputs at the B200 launch geometry and
 reports whether - and where - the two sequences part.
@@ -46,5 +46,13 @@ print('C3 emulated kernels: %.1f s, identical: %s' % (time.time() - t, np.array_
 if not np.array_equal(sim, out['c3_idx']):
     print('   first divergence at step', int(np.flatnonzero(sim != out['c3_idx'])[0]))
 out['c3_idx_kernels'] = sim
+c = synthetic.config_c5()          # d = 64: the oracle needs ~20 minutes for the 500 steps
+t = time.time()
+out['c5_idx'] = ot.thin(c['sample'], c['gradient'], c['m'], preconditioner='med')
+print('C5 oracle: %.1f s, %d unique of %d' % (time.time() - t, len(np.unique(out['c5_idx'])), c['m']), flush=True)
+t = time.time()
+sim = H.SimProblem(c['sample'], c['gradient'], preconditioner='med').thin(c['m'])[0]
+print('C5 emulated kernels: %.1f s, identical: %s' % (time.time() - t, np.array_equal(sim, out['c5_idx'])), flush=True)
+out['c5_idx_kernels'] = sim
 np.savez_compressed(os.path.join(HERE, 'full_size_indices.npz'), **out)
 print('wrote', os.path.join(HERE, 'full_size_indices.npz'))

@@ -1,5 +1,5 @@
-"""BASELINE configs C2 and C3 at FULL size and FULL length on the GPU: all m = 1000 selected indices against the numpy
-oracle's sequence, precomputed by tests/golden/make_golden_full.py (the oracle needs 35 s / 170 s at these sizes).
+"""BASELINE configs C2, C3 and C5 at FULL size and FULL length on the GPU: every selected index against the numpy
+oracle's sequence, precomputed by tests/golden/make_golden_full.py (the oracle needs 35 s / 170 s / 19 min at these sizes).
 The same script ran the emulator build of the kernels at the B200 launch geometry: identical sequences, and since the
 strict float64 mode uses IEEE operations only, that is a prediction of what the device returns.
 
@@ -37,3 +37,12 @@ def test_c3_full_sequence_matches_numpy(gpu_device, golden):
                    precision='f64-fast', device=gpu_device)
     same = int(np.argmax(np.concatenate([fast != golden['c3_idx'], [True]])))
     assert same >= 100, same          # the FMA formulation may part from numpy at a near-tie, not early
+
+
+def test_c5_full_sequence_matches_numpy(gpu_device, golden):
+    """d = 64 (the HBM-streaming step kernel), n = 5 x 10^5, all 500 selections; the oracle needed 19 minutes."""
+    from gradient_free_mcmc_postprocessing_b200 import synthetic
+    from gradient_free_mcmc_postprocessing_b200.thinning import thin
+    c = synthetic.config_c5()
+    idx = thin(c['sample'], c['gradient'], c['m'], preconditioner='med', device=gpu_device)
+    assert np.array_equal(idx, golden['c5_idx']), np.flatnonzero(idx != golden['c5_idx'])[:3]
