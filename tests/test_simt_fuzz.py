@@ -70,3 +70,66 @@ def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fas
     finally:
         for k in ('GFK_PERSISTENT', 'GFK_RESIDENT', 'SIMT_SMS'):
             os.environ.pop(k, None)
+
+
+@settings(max_examples=int(os.environ.get('GFK_FUZZ_EXAMPLES', '25')), derandomize='GFK_FUZZ_EXAMPLES' not in os.environ,
+          deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(2, 400), d=st.integers(1, 40), m=st.integers(1, 300),
+       gf=st.booleans(), n_parts=st.integers(1, 4), precision=st.sampled_from(['f64', 'f64-fast']), ws=st.booleans(),
+       sms=st.integers(1, 6))
+def test_ksd_of_a_selection_matches_oracle(seed, n, d, m, gf, n_parts, precision, ws, sms):
+    """Cumulative KSD of m selected rows (with repeats), the triangle dealt over 1-4 parts, tile and warp-specialised
+    kernels - against the oracle's ksd of the re-indexed integrand."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)) + rng.standard_normal(d)
+    g = -(x - x.mean(0)) * (1.0 + 0.1 * np.arange(d))
+    log_p = -0.5 * np.sum((x - x.mean(0)) ** 2, axis=1) / d
+    log_q = log_p + np.sin(x[:, 0])
+    sel = rng.integers(0, n, m)
+    os.environ['SIMT_SMS'] = str(sms)
+    os.environ['GFK_KSD_WS'] = '1' if ws else '0'
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            if gf:
+                ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med')
+                p = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision)
+            else:
+                ref = ot._make_stein_integrand(x, g, preconditioner='med')
+                p = H.SimProblem(x, g, preconditioner='med', precision=precision)
+        want = os_.ksd(lambda a, b: ref(sel[a], sel[b]), m)
+        np.testing.assert_allclose(p.ksd(sel=sel, n_parts=n_parts), want, rtol=1e-10)
+    finally:
+        for k in ('SIMT_SMS', 'GFK_KSD_WS'):
+            os.environ.pop(k, None)
+
+
+@settings(max_examples=int(os.environ.get('GFK_FUZZ_EXAMPLES', '25')), derandomize='GFK_FUZZ_EXAMPLES' not in os.environ,
+          deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(2, 700), m=st.integers(1, 500), d=st.integers(1, 8),
+       weighted=st.booleans(), sms=st.integers(1, 8))
+def test_kde_and_energy_match_scipy(seed, n, m, d, weighted, sms):
+    from scipy.spatial.distance import cdist
+    from scipy.stats import gaussian_kde
+    rng = np.random.default_rng(seed)
+    data = rng.standard_normal((n, d)) @ (np.eye(d) + 0.3 * rng.standard_normal((d, d)))
+    pts = rng.standard_normal((m, d)) * 1.5
+    if n <= d or np.linalg.cond(np.cov(data, rowvar=False).reshape(d, d)) > 1e6:
+        return                                # (near-)singular bandwidth matrix: conditioning, not the kernels, decides
+    w = rng.random(n) + 0.05 if weighted else None
+    os.environ['SIMT_SMS'] = str(sms)
+    try:
+        log_q, grad_q = H.kde_proxy(data, weights=w, points=pts)
+        kde = gaussian_kde(data.T, bw_method='silverman', weights=w)
+        np.testing.assert_allclose(log_q, kde.logpdf(pts.T), rtol=1e-11, atol=1e-10)
+        eps = 1e-6                                                   # gradient against central differences
+        num = np.stack([(kde.logpdf((pts + eps * np.eye(d)[k]).T) - kde.logpdf((pts - eps * np.eye(d)[k]).T)) / (2 * eps)
+                        for k in range(d)], axis=1)
+        np.testing.assert_allclose(grad_q, num, rtol=2e-4, atol=2e-4 * max(1.0, np.abs(num).max()))
+        e2 = H.energy_cumulative(data, pts)
+        for t in {0, m // 2, m - 1}:
+            y = pts[:t + 1]
+            want = 2 * cdist(data, y).mean() - cdist(data, data).mean() - cdist(y, y).mean()
+            assert abs(e2[t] - want) <= 1e-11 * max(1.0, abs(want))
+    finally:
+        os.environ.pop('SIMT_SMS', None)
