@@ -855,6 +855,127 @@ __global__ void __launch_bounds__(kThreads, 1) thin_step_chunked_pipe_kernel(Thi
     grid_argmin_publish(bv, bi, a);
 }
 
+// ---- tensor memory as a row store -----------------------------------------------------------------------------
+// sm_100a has 256 KB of tensor memory (TMEM) per SM - 512 columns x 128 lanes x 32 bit - next to the 227 KB of shared
+// memory; it is private to the CTA, read and written with tcgen05.ld / tcgen05.st (12-cycle latency, 64 B / clock
+// per SM).  The single-launch kernel is bound by re-reading from L2, every step, the rows that do not fit in shared
+// memory; parking another 8 rows per thread (d = 4; 16 for d = 2) in TMEM takes C3 from 3 to 11 of 14 rows on chip.
+// Layout: warp w may touch lanes 32 (w % 4) .. + 31 only, so the four warps sharing a lane quarter each get 128 of
+// the 512 columns; with the .32x32b shape thread i of a warp owns lane 32 (w % 4) + i, and one row (x and s, 2 D
+// doubles = 4 D columns) is one tcgen05.ld.  All TMEM instructions are .sync.aligned: they sit in passes where every
+// thread of the grid owns a row, outside any divergent branch.
+// [round 1: opt-in with GFK_TMEM=1; executed on the CPU emulator of the test suite only, not yet on a GPU]
+constexpr int kTmemCols = 512;
+
+__device__ __forceinline__ void tmem_alloc_all(uint32_t* dst_smem) {      // one full warp
+#if defined(GFK_SIMT_HOST)
+    simt::tmem_alloc(dst_smem, kTmemCols);
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_free_all(uint32_t base) {            // the same warp
+#if defined(GFK_SIMT_HOST)
+    simt::tmem_dealloc(base, kTmemCols);
+#else
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(kTmemCols) : "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_fence_before_sync() {
+#if !defined(GFK_SIMT_HOST)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_fence_after_sync() {
+#if !defined(GFK_SIMT_HOST)
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_wait_st() {
+#if !defined(GFK_SIMT_HOST)
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+#if !defined(GFK_SIMT_HOST)
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+#if defined(GFK_SIMT_HOST)
+    simt::tmem_st(taddr, r, 16);
+#else
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+#if defined(GFK_SIMT_HOST)
+    simt::tmem_ld(taddr, r, 16);
+#else
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+#if defined(GFK_SIMT_HOST)
+    simt::tmem_st(taddr, r, 8);
+#else
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+#endif
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+#if defined(GFK_SIMT_HOST)
+    simt::tmem_ld(taddr, r, 8);
+#else
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#endif
+}
+
+// one row (x[D], s[D] in float64; D = 2 or 4) <-> 4 D tensor-memory columns of this thread's lane
+template <int D>
+__device__ __forceinline__ void tmem_put_row(uint32_t taddr, const double (&x)[D], const double (&sx)[D]) {
+    static_assert(D == 2 || D == 4, "tensor-memory row store: d = 2 or 4");
+    uint32_t r[4 * D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const unsigned long long xb = (unsigned long long)__double_as_longlong(x[k]);
+        const unsigned long long sb = (unsigned long long)__double_as_longlong(sx[k]);
+        r[2 * k] = (uint32_t)xb;
+        r[2 * k + 1] = (uint32_t)(xb >> 32);
+        r[2 * D + 2 * k] = (uint32_t)sb;
+        r[2 * D + 2 * k + 1] = (uint32_t)(sb >> 32);
+    }
+    if constexpr (D == 4) tmem_st16(taddr, r);
+    else tmem_st8(taddr, r);
+}
+template <int D>
+__device__ __forceinline__ void tmem_get_row(uint32_t taddr, double (&x)[D], double (&sx)[D]) {
+    static_assert(D == 2 || D == 4, "tensor-memory row store: d = 2 or 4");
+    uint32_t r[4 * D];
+    if constexpr (D == 4) tmem_ld16(taddr, r);
+    else tmem_ld8(taddr, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        x[k] = __longlong_as_double((long long)(((unsigned long long)r[2 * k + 1] << 32) | r[2 * k]));
+        sx[k] = __longlong_as_double((long long)(((unsigned long long)r[2 * D + 2 * k + 1] << 32) | r[2 * D + 2 * k]));
+    }
+}
+// float rows are never parked in tensor memory (the template flag is only instantiated for float64)
+template <int D>
+__device__ __forceinline__ void tmem_put_row(uint32_t, const float (&)[D], const float (&)[D]) {}
+template <int D>
+__device__ __forceinline__ void tmem_get_row(uint32_t, float (&)[D], float (&)[D]) {}
+
 // ---- all m greedy steps in ONE cooperative launch (single rank, small D) -------------------------------
 // One CTA per SM (or fewer for small shards).  Thread g of the grid owns rows g, g + T, g + 2T, ... for the
 // whole job (T = threads in the grid).  The running objective A and the log-weights of the owned rows live
@@ -867,8 +988,10 @@ constexpr int kPersistThreads = 512;
 constexpr int kPollPerLane = 5;                       // persistent grid <= 160 CTAs (one per SM)
 
 // WDD (strict mode only): gradient-free weights from the per-row double-double exponentials in a.w (exp_sum_dd)
-template <typename T, int D, bool STRICT, bool MULTI, bool WDD>
-__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res) {
+// TM: passes [rpt_res, rpt_res + rpt_tm) of every thread's rows are parked in tensor memory (float64, d = 2 or 4)
+template <typename T, int D, bool STRICT, bool MULTI, bool WDD, bool TM>
+__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res,
+                                                                             int rpt_tm) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double sv[32];
     __shared__ unsigned si[32];
@@ -895,6 +1018,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     const bool use_w = (!STRICT && a.w != nullptr);
     ThinWs* ws = a.ws;
     if (tid == 0) abort_sh = 0;
+    __shared__ uint32_t tmem_base_sh;
+    uint32_t my_taddr = 0;
+    if constexpr (TM) {
+        if (tid < 32) tmem_alloc_all(&tmem_base_sh);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        // lanes 32 (warp % 4) .. + 31, columns 128 (warp / 4) .. + 127 belong to this warp
+        my_taddr = tmem_base_sh + ((uint32_t)((tid >> 5) & 3) * 32u << 16) + (uint32_t)(tid >> 7) * 128u;
+    }
 
     // ---- step 0: diagonal, and stage the owned rows ----------------------------------------------------
     double bv = __longlong_as_double(0x7ff0000000000000LL);
@@ -935,6 +1068,18 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
             A_sh[slot] = k0;
             if (cand_better_in_order(k0, bv, bi == 0xffffffffu)) { bv = k0; bi = (unsigned)i; }   // rows in increasing order
         }
+    }
+
+    if constexpr (TM) {
+        // park the rows of the full passes [rpt_res, rpt_res + rpt_tm) in tensor memory (every thread owns a row there)
+        for (int jt = 0; jt < rpt_tm; ++jt) {
+            const long long i = a.row_begin + (long long)(rpt_res + jt) * TT + gt;
+            T xr[D], sr[D];
+            load_row<D>(a.x, i, xr);
+            load_row<D>(a.s, i, sr);
+            tmem_put_row<D>(my_taddr + (uint32_t)(jt * 4 * D), xr, sr);
+        }
+        tmem_wait_st();
     }
 
     for (int step = 0; step < m; ++step) {
@@ -1096,8 +1241,19 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 update_row(i, slot, xr, sr);
             }
         }
+        int j_stream = rpt_res;
+        if constexpr (TM) {
+            // rows parked in tensor memory: full passes only, so no thread sits out and the warp stays converged
 #pragma unroll 2
-        for (int j = rpt_res; j < rpt; ++j, i_cur += TT, slot += nthr) {
+            for (int jt = 0; jt < rpt_tm; ++jt, i_cur += TT, slot += nthr) {
+                T xr[D], sr[D];
+                tmem_get_row<D>(my_taddr + (uint32_t)(jt * 4 * D), xr, sr);
+                update_row(i_cur, slot, xr, sr);
+            }
+            j_stream += rpt_tm;
+        }
+#pragma unroll 2
+        for (int j = j_stream; j < rpt; ++j, i_cur += TT, slot += nthr) {
             const long long i = (j == rpt - 1) ? i_last : i_cur;
             if (i < a.row_end) {
                 T xr[D], sr[D];
@@ -1111,6 +1267,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     for (int j = 0; j < rpt; ++j) {
         const long long li = (j == rpt - 1) ? last_base + last_e : (long long)j * TT + gt;
         if (li < rows) a.A[li] = A_sh[j * nthr + tid];
+    }
+    if constexpr (TM) {
+        tmem_fence_before_sync();
+        __syncthreads();                       // every warp is done with its tensor-memory rows
+        tmem_fence_after_sync();
+        if (tid < 32) tmem_free_all(tmem_base_sh);
     }
 }
 
@@ -1214,16 +1376,35 @@ static cudaError_t launch_cooperative(void (*kernel)(KArgs...), unsigned grid, i
 }
 
 // one instantiation of the single-launch kernel: opt-in shared memory, reset, cooperative launch
-template <typename T, int D, bool STRICT, bool MULTI, bool WDD>
-static int persistent_go(const ThinArgs<T>& a, const MailArgs& mail, int m, int rpt, int rpt_res, unsigned grid,
-                         int threads, size_t smem, cudaStream_t st) {
-    cudaError_t e = persistent_prepare(thin_persistent_kernel<T, D, STRICT, MULTI, WDD>, threads, smem);
+template <typename T, int D, bool STRICT, bool MULTI, bool WDD, bool TM>
+static int persistent_go2(const ThinArgs<T>& a, const MailArgs& mail, int m, int rpt, int rpt_res, int rpt_tm,
+                          unsigned grid, int threads, size_t smem, cudaStream_t st) {
+    cudaError_t e = persistent_prepare(thin_persistent_kernel<T, D, STRICT, MULTI, WDD, TM>, threads, smem);
     if (e != cudaSuccess) return 0;
     thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail);
-    e = launch_cooperative(thin_persistent_kernel<T, D, STRICT, MULTI, WDD>, grid, threads, smem, st, a, m, rpt, rpt_res);
+    e = launch_cooperative(thin_persistent_kernel<T, D, STRICT, MULTI, WDD, TM>, grid, threads, smem, st, a, m, rpt,
+                           rpt_res, rpt_tm);
     if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
     count_launches(2);
     return 1;
+}
+
+// GFK_TMEM=1 (opt-in): park as many full passes of rows as fit in tensor memory (float64, d = 2 or 4)
+template <typename T, int D, bool STRICT, bool MULTI, bool WDD>
+static int persistent_go(const ThinArgs<T>& a, const MailArgs& mail, int m, int rpt, int rpt_res, unsigned grid,
+                         int threads, size_t smem, cudaStream_t st) {
+    if constexpr (std::is_same<T, double>::value && (D == 2 || D == 4)) {
+        const char* env = getenv("GFK_TMEM");
+        if (env && env[0] == '1' && threads == kPersistThreads) {
+            const int slots = (kTmemCols / 4) / (4 * D);          // 128 columns per warp / columns per row
+            int rpt_tm = rpt - 1 - rpt_res;                       // full passes after the shared-memory ones
+            if (rpt_tm > slots) rpt_tm = slots;
+            if (rpt_tm > 0)
+                return persistent_go2<T, D, STRICT, MULTI, WDD, true>(a, mail, m, rpt, rpt_res, rpt_tm, grid, threads,
+                                                                      smem, st);
+        }
+    }
+    return persistent_go2<T, D, STRICT, MULTI, WDD, false>(a, mail, m, rpt, rpt_res, 0, grid, threads, smem, st);
 }
 
 // persistent path: returns 1 if it ran, 0 if not eligible, < 0 on error

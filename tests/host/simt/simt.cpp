@@ -92,6 +92,8 @@ struct Block {
     const std::function<void()>* fn = nullptr;
     bool failed = false;
     unsigned polls = 0;
+    std::vector<unsigned> tmem;         // 128 lanes x 512 columns once allocated
+    int tmem_cols = 0;                  // allocated columns (0: none)
     const char* site_file = nullptr;   // call site of the __syncthreads being collected
     int site_line = 0;
 };
@@ -225,6 +227,61 @@ const unsigned long long* warp_gather(unsigned long long bits) {
 // the lanes that took part in this thread's most recent collective (lanes that exit later must still count)
 unsigned warp_alive_mask() { return t_blk->running->last_mask; }
 
+// all 32 lanes of the warp must execute the instruction together with the same operand (.sync.aligned)
+static void warp_converged(unsigned operand, const char* what) {
+    const unsigned long long* all = warp_gather(operand);
+    Block* b = t_blk;
+    if (warp_alive_mask() != 0xffffffffu) fail("%s by a warp with exited lanes", what);
+    for (int l = 0; l < 32; ++l)
+        if ((unsigned)all[l] != operand) fail("%s with lane-dependent operand (%u vs %u)", what, (unsigned)all[l], operand);
+    (void)b;
+}
+
+void tmem_alloc(unsigned* dst_smem, int cols) {
+    warp_converged((unsigned)cols, "tcgen05.alloc");
+    Block* b = t_blk;
+    if (cols < 32 || cols > 512 || (cols & (cols - 1))) fail("tcgen05.alloc of %d columns", cols);
+    if (b->running->lane == 0) {
+        if (b->tmem_cols) fail("tcgen05.alloc while tensor memory is already allocated");
+        b->tmem.assign(128 * 512, 0xdeadbeefu);
+        b->tmem_cols = cols;
+        *dst_smem = 0u;                                    // base address: lane 0, column 0
+    }
+}
+
+void tmem_dealloc(unsigned base, int cols) {
+    warp_converged(base, "tcgen05.dealloc");
+    Block* b = t_blk;
+    if (b->running->lane == 0) {
+        if (!b->tmem_cols || cols != b->tmem_cols || base != 0u) fail("tcgen05.dealloc does not match the allocation");
+        b->tmem_cols = 0;
+    }
+}
+
+static std::atomic<long long> g_tmem_accesses{0};
+
+static unsigned* tmem_row(unsigned taddr, int n, const char* what) {
+    warp_converged(taddr, what);
+    g_tmem_accesses.fetch_add(1, std::memory_order_relaxed);
+    Block* b = t_blk;
+    Fiber* f = b->running;
+    const unsigned lane_base = taddr >> 16, col = taddr & 0xffffu;
+    if (!b->tmem_cols) fail("%s without a tensor-memory allocation", what);
+    if (lane_base != (unsigned)(f->warp % 4) * 32u) fail("%s: warp %d may not access lanes from %u", what, f->warp, lane_base);
+    if (col + (unsigned)n > (unsigned)b->tmem_cols) fail("%s: columns %u..%u beyond the %d allocated", what, col, col + n, b->tmem_cols);
+    return b->tmem.data() + (size_t)(lane_base + (unsigned)f->lane) * 512 + col;
+}
+
+void tmem_st(unsigned taddr, const unsigned* regs, int n) {
+    unsigned* row = tmem_row(taddr, n, "tcgen05.st");
+    for (int c = 0; c < n; ++c) row[c] = regs[c];
+}
+
+void tmem_ld(unsigned taddr, unsigned* regs, int n) {
+    const unsigned* row = tmem_row(taddr, n, "tcgen05.ld");
+    for (int c = 0; c < n; ++c) regs[c] = row[c];
+}
+
 void cp_async(void* dst, const void* src, int bytes) {
     Fiber* f = t_blk->running;
     check_align(dst, (size_t)bytes, "cp.async destination");
@@ -322,6 +379,7 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
     b.failed = false;
     b.warps.assign((size_t)nwarps, WarpState());
     for (NamedBarrier& nb : b.named) nb = NamedBarrier();
+    b.tmem_cols = 0;
     if (smem_bytes) memset(b.smem, 0xff, smem_bytes);   // poison: NaN patterns / huge integers
     uint3 bid;
     bid.x = linear_block % grid.x;
@@ -391,6 +449,10 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
         b.running = &f;
         simt_switch(&b.sched_sp, f.sp);
         b.running = nullptr;
+    }
+    if (!b.failed && b.tmem_cols) {
+        record_error("block exited without tcgen05.dealloc: tensor memory would stay allocated on the SM");
+        b.tmem_cols = 0;
     }
     if (!b.failed) {
         for (int id = 1; id < 16; ++id) {
@@ -462,6 +524,9 @@ void launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::fun
 }
 
 }  // namespace simt
+
+// test observation: tcgen05.ld / tcgen05.st executed so far (per thread)
+extern "C" long long simt_tmem_access_count(void) { return simt::g_tmem_accesses.load(); }
 
 // test control: scheduling order of the emulated threads (0 round-robin, 1 random with `seed`)
 extern "C" void simt_set_schedule(int random, unsigned seed) {

@@ -63,6 +63,12 @@ void poll_yield();                      // inside spin loops on memory another t
 // cp.async with its real (deferred) semantics: the bytes move no earlier than the cp_async_wait that covers their
 // group, so reading a staged buffer before waiting - or before the barrier that publishes OTHER threads' waits -
 // finds the poison pattern instead of data
+// tensor memory (sm_100a): 512 columns x 128 lanes x 32 bit per CTA; tcgen05.alloc / dealloc by one full warp,
+// tcgen05.st / ld.32x32b.xN by full, converged warps that may only touch lanes 32 (warp % 4) .. + 31
+void tmem_alloc(unsigned* dst_smem, int cols);
+void tmem_dealloc(unsigned base, int cols);
+void tmem_st(unsigned taddr, const unsigned* regs, int n);
+void tmem_ld(unsigned taddr, unsigned* regs, int n);
 void cp_async(void* dst, const void* src, int bytes);
 void cp_async_commit();
 void cp_async_wait(int allow_pending_groups);

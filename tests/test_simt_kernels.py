@@ -6,6 +6,7 @@ block / grid reductions, tie-breaking, the flag-in-data grid exchange of the sin
 says nothing about device arithmetic that differs from the host's (CUDA's exp / rsqrt), which the `-m gpu` tests
 cover.  With the host's exact reciprocal square root the strict mode must reproduce the oracle's indices exactly.
 """
+import ctypes
 import os
 import warnings
 
@@ -650,3 +651,38 @@ def test_full_size_c3_on_the_b200_grid_shape(monkeypatch):
         p = H.SimProblem(c['sample'], c['gradient_q'], c['log_p'], c['log_q'], preconditioner='med', precision=precision)
         idx, _ = p.thin(m)
         assert np.array_equal(idx, expect), precision
+
+
+@pytest.mark.parametrize('d', [2, 4])
+def test_tensor_memory_row_store_equals_the_default_kernel(d, monkeypatch):
+    """GFK_TMEM=1: full passes of rows parked in tensor memory (tcgen05.st once, tcgen05.ld every step; the emulator
+    checks the lane-quarter rule, convergence of the .sync.aligned instructions, allocation bounds and the final
+    dealloc).  Indices and the final objective must be bit-identical to the default kernel and equal the oracle."""
+    monkeypatch.setenv('SIMT_SMS', '2')
+    rng = np.random.default_rng(9100 + d)
+    n = 11 * 1024 + 333                                         # 12 passes: some in shared memory, 7 in TMEM, 1 streamed
+    x, g = _mcmc_like(rng, n, d)
+    log_p = -0.5 * np.sum(x ** 2, axis=1)
+    log_q = log_p + 0.5 * np.sin(x[:, 0])
+    m = 6
+    expect = ot.thin_gf(x, log_p, log_q, g, m, preconditioner='med')
+    for precision in ('f64', 'f64-fast'):
+        monkeypatch.delenv('GFK_TMEM', raising=False)
+        base = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(m)
+        monkeypatch.setenv('GFK_TMEM', '1')
+        lib = H.load()
+        lib.simt_tmem_access_count.restype = ctypes.c_longlong
+        for random, seed in ((False, 0), (True, 3)):
+            H.set_schedule(random, seed)
+            before = lib.simt_tmem_access_count()
+            idx, obj = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(m)
+            assert np.array_equal(idx, base[0]) and np.array_equal(obj, base[1]), (precision, random)
+            # (passes in tensor memory) x 1024 threads: one store each, one load per greedy update; 7 passes at d = 4
+            passes, rem = divmod(lib.simt_tmem_access_count() - before, 1024 * m)
+            assert rem == 0 and passes == (7 if d == 4 else 3)
+        H.set_schedule(False)
+        assert np.array_equal(base[0], expect), precision
+    # score-based kernel and a shard that fits shared memory entirely (no tensor-memory pass: falls back silently)
+    monkeypatch.setenv('GFK_TMEM', '1')
+    assert np.array_equal(H.SimProblem(x, g, preconditioner='med').thin(m)[0], ot.thin(x, g, m, preconditioner='med'))
+    assert np.array_equal(H.SimProblem(x[:900], g[:900]).thin(m)[0], ot.thin(x[:900], g[:900], m))

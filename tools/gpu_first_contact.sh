@@ -12,6 +12,11 @@ echo "== bench"; timeout 400 python bench.py > gpurun_out/bench_n1.log 2> gpurun
 echo "== bench reference arm"; timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; echo "rc=$?"
 echo "== probes"; timeout 400 python tools/gpu_probe.py > gpurun_out/probe.log 2>&1; echo "rc=$?"
 timeout 400 python tools/next_rows_probe.py > gpurun_out/next_rows_probe.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/next_rows_probe.log
+echo "== A/B: tensor-memory row store (opt-in, own process + timeout: first run of tcgen05.ld/st on a device)"
+AB_TAG=default timeout 200 python tools/ab_probe.py > gpurun_out/ab_tmem.log 2>&1; echo "rc=$?"
+AB_TAG=tmem GFK_TMEM=1 timeout 200 python tools/ab_probe.py >> gpurun_out/ab_tmem.log 2>&1; echo "rc=$?"
+GFK_TMEM=1 timeout 300 python -m pytest tests/test_zy_full_size_golden.py -m gpu -x -q >> gpurun_out/ab_tmem.log 2>&1; echo "rc=$?"
+cat gpurun_out/ab_tmem.log | tail -20
 echo "== per-phase trace of the persistent kernel (needs: GFK_TRACE=1 bash gradient_free_mcmc_postprocessing_b200/csrc/build.sh)"
 if [ -f libgfk_trace.so ]; then
     for cfg in "c3 f64" "c3 f64-fast" "c2 f64"; do
