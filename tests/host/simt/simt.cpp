@@ -546,7 +546,9 @@ const char* cudaGetErrorString(cudaError_t e) {
     }
 }
 cudaError_t cudaGetLastError() { return simt::g_last_error.exchange(0); }
-cudaError_t cudaGetDevice(int* dev) { *dev = 0; return cudaSuccess; }
+// libgfk caches the SM count per device id: the emulated "device id" is the emulated SM count, so a test that changes
+// SIMT_SMS really gets the new launch geometry
+cudaError_t cudaGetDevice(int* dev) { *dev = simt::env_int("SIMT_SMS", 4); return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
     switch (a) {
         case cudaDevAttrMultiProcessorCount: *v = simt::env_int("SIMT_SMS", 4); return cudaSuccess;
