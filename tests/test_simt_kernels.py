@@ -649,8 +649,10 @@ def test_full_size_c3_on_the_b200_grid_shape(monkeypatch):
     assert np.array_equal(golden['c3_idx'], golden['c3_idx_kernels']) and np.array_equal(golden['c2_idx'], golden['c2_idx_kernels'])
     for precision in ('f64', 'f64-fast'):
         p = H.SimProblem(c['sample'], c['gradient_q'], c['log_p'], c['log_q'], preconditioner='med', precision=precision)
-        idx, _ = p.thin(m)
-        assert np.array_equal(idx, expect), precision
+        for tmem in ('0', '1'):                  # 1: 8 of every thread's 14 rows parked in tensor memory (opt-in)
+            monkeypatch.setenv('GFK_TMEM', tmem)
+            idx, _ = p.thin(m)
+            assert np.array_equal(idx, expect), (precision, tmem)
 
 
 @pytest.mark.parametrize('d', [2, 4])
