@@ -5,6 +5,7 @@ PyTorch is used only to own device buffers and streams; every arithmetic step of
 is a libgfk call.  Nothing here falls back to the CPU.
 """
 import ctypes
+import os
 import warnings
 
 import numpy as np
@@ -249,7 +250,8 @@ class SteinProblem:
             ws = _bytes(lib.gfk_log_weights_ws_bytes(), self.device)
             check(lib.gfk_log_weights_range(_ptr(klw), self.n, rng, _ptr(ws), st))
             self.lw_range = (rng[0], rng[1])
-            if -EXP_DD_LIMIT <= rng[0] and rng[1] <= EXP_DD_LIMIT:
+            # GFK_EXP_DD=0: keep the device exp (A/B measurements only)
+            if -EXP_DD_LIMIT <= rng[0] and rng[1] <= EXP_DD_LIMIT and os.environ.get('GFK_EXP_DD', '1') != '0':
                 self.w = torch.empty((self.n, 2), dtype=torch.float64, device=self.device)
                 check(lib.gfk_exp_weights_dd(_ptr(klw), _ptr(self.w), self.n, st))
         self._kx, self._ks, self._klw, self._kxl = kx, ks, klw, kxl

@@ -1643,6 +1643,9 @@ extern "C" int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end
             GFK_REQUIRE(reinterpret_cast<uintptr_t>(p->x) % 8 == 0 && reinterpret_cast<uintptr_t>(p->s) % 8 == 0,
                         "gfk_thin: x and s must be 8-byte aligned for d = %d", p->d);
     }
+    if (p->mode == GFK_F64_STRICT && p->lw && p->w)
+        GFK_REQUIRE(reinterpret_cast<uintptr_t>(p->w) % 16 == 0,
+                    "gfk_thin: in the strict mode w holds (hi, lo) pairs and must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (p->mode) {
         case GFK_F64_STRICT: return thin_typed<double, true>(p, row_begin, row_end, m, objective, idx_out, ws, st);

@@ -1,4 +1,5 @@
-"""A/B timing of libgfk builds (GFK_LIB=<path>): C1/C2/C3 thinning us/step.  Development tool."""
+"""A/B timing of libgfk builds (GFK_LIB=<path>) or switches (GFK_TMEM=1, GFK_EXP_DD=0, ...): C1/C2/C3 thinning
+us/step.  Development tool."""
 import os, sys, time, warnings
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -15,6 +15,7 @@ timeout 400 python tools/next_rows_probe.py > gpurun_out/next_rows_probe.log 2>&
 echo "== A/B: tensor-memory row store (opt-in, own process + timeout: first run of tcgen05.ld/st on a device)"
 AB_TAG=default timeout 200 python tools/ab_probe.py > gpurun_out/ab_tmem.log 2>&1; echo "rc=$?"
 AB_TAG=tmem GFK_TMEM=1 timeout 200 python tools/ab_probe.py >> gpurun_out/ab_tmem.log 2>&1; echo "rc=$?"
+AB_TAG=device-exp GFK_EXP_DD=0 timeout 200 python tools/ab_probe.py >> gpurun_out/ab_tmem.log 2>&1; echo "rc=$?"
 GFK_TMEM=1 timeout 300 python -m pytest tests/test_zy_full_size_golden.py -m gpu -x -q >> gpurun_out/ab_tmem.log 2>&1; echo "rc=$?"
 cat gpurun_out/ab_tmem.log | tail -20
 echo "== per-phase trace of the persistent kernel (needs: GFK_TRACE=1 bash gradient_free_mcmc_postprocessing_b200/csrc/build.sh)"
