@@ -18,7 +18,7 @@ pids=()
 for f in api comm prep thin ksd proxy energy ${GFK_SIM_EXTRA_UNITS:-}; do
     [ -f "${csrc}/${f}.cu" ] || continue
     python "${here}/simt/cu2cpp.py" "${csrc}/${f}.cu" "${gen}/${f}.cpp"
-    g++ -std=c++17 -O2 -g -ffp-contract=off -fPIC -DGFK_SIMT_HOST=1 -Wno-unknown-pragmas -Wno-attributes \
+    g++ -std=c++17 -O2 -g -ffp-contract=off -fPIC -DGFK_SIMT_HOST=1 -Wno-unknown-pragmas -Wno-attributes ${GFK_SIM_CXXFLAGS:-} \
         -I"${here}/simt/include" -I"${csrc}" -c "${gen}/${f}.cpp" -o "${gen}/${f}.o" &
     pids+=($!)
 done
@@ -30,6 +30,6 @@ g++ -std=c++17 -O2 -g -fPIC -DGFK_SIMT_HOST=1 -Wno-unknown-pragmas -I"${here}/si
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 for f in api comm prep thin ksd proxy energy ${GFK_SIM_EXTRA_UNITS:-} simt selftest; do [ -f "${gen}/${f}.o" ] && objs+=("${gen}/${f}.o"); done
-g++ -shared -o "${here}/libgfk_sim.so" "${objs[@]}" -ldl -lpthread -lrt
+g++ -shared ${GFK_SIM_CXXFLAGS:-} -o "${here}/libgfk_sim.so" "${objs[@]}" -ldl -lpthread -lrt
 g++ -std=c++17 -O2 -g -fPIC -shared -o "${here}/libfake_nccl.so" "${here}/simt/fake_nccl.cpp" -lrt -lpthread
 echo "built ${here}/libgfk_sim.so"
