@@ -988,7 +988,8 @@ constexpr int kPersistThreads = 512;
 constexpr int kPollPerLane = 5;                       // persistent grid <= 160 CTAs (one per SM)
 
 // WDD (strict mode only): gradient-free weights from the per-row double-double exponentials in a.w (exp_sum_dd)
-// TM: passes [rpt_res, rpt_res + rpt_tm) of every thread's rows are parked in tensor memory (float64, d = 2 or 4)
+// TM: passes [0, rpt_tm) of every thread's rows are parked in tensor memory (float64, d = 2 or 4), the next rpt_res
+// passes in shared memory, the rest streams through L2
 template <typename T, int D, bool STRICT, bool MULTI, bool WDD, bool TM>
 __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res,
                                                                              int rpt_tm) {
@@ -1012,7 +1013,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     const int slots = rpt * nthr;
     double* A_sh = reinterpret_cast<double*>(psm);
     T* lw_sh = reinterpret_cast<T*>(A_sh + slots);              // lw (strict / no w) or w (fast)
-    const int slots_res = rpt_res * nthr;                        // the first rpt_res rows of every thread
+    const int slots_res = rpt_res * nthr;                        // rpt_res passes of every thread's rows
+    const int j0_res = TM ? rpt_tm : 0;                          // passes [0, rpt_tm): tensor memory; then shared memory
     T* xs = lw_sh + (a.lw ? slots : 0);                          // resident x as [D][slots_res], then s
     T* ss = xs + (size_t)D * slots_res;
     const bool use_w = (!STRICT && a.w != nullptr);
@@ -1040,9 +1042,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
             T xr[D], sr[D];
             load_row<D>(a.x, i, xr);
             load_row<D>(a.s, i, sr);
-            if (j < rpt_res) {
+            if (j >= j0_res && j < j0_res + rpt_res) {
+                const int rs = slot - j0_res * nthr;
 #pragma unroll
-                for (int k = 0; k < D; ++k) { xs[k * slots_res + slot] = xr[k]; ss[k * slots_res + slot] = sr[k]; }
+                for (int k = 0; k < D; ++k) { xs[k * slots_res + rs] = xr[k]; ss[k * slots_res + rs] = sr[k]; }
             }
             double k0;
             if constexpr (STRICT) k0 = pair_strict<D>(xr, xr, sr, sr, a.kp);
@@ -1071,9 +1074,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     }
 
     if constexpr (TM) {
-        // park the rows of the full passes [rpt_res, rpt_res + rpt_tm) in tensor memory (every thread owns a row there)
+        // park the rows of the full passes [0, rpt_tm) in tensor memory (every thread owns a row there)
         for (int jt = 0; jt < rpt_tm; ++jt) {
-            const long long i = a.row_begin + (long long)(rpt_res + jt) * TT + gt;
+            const long long i = a.row_begin + (long long)jt * TT + gt;
             T xr[D], sr[D];
             load_row<D>(a.x, i, xr);
             load_row<D>(a.s, i, sr);
@@ -1231,17 +1234,6 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         // round-robin dealing (i_last).  Rows are visited in increasing index order (cand_better_in_order).
         long long i_cur = a.row_begin + gt;
         int slot = tid;
-#pragma unroll 2
-        for (int j = 0; j < rpt_res; ++j, i_cur += TT, slot += nthr) {
-            const long long i = (j == rpt - 1) ? i_last : i_cur;
-            if (i < a.row_end) {
-                T xr[D], sr[D];
-#pragma unroll
-                for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots_res + slot]; sr[k] = ss[k * slots_res + slot]; }
-                update_row(i, slot, xr, sr);
-            }
-        }
-        int j_stream = rpt_res;
         if constexpr (TM) {
             // rows parked in tensor memory: full passes only, so no thread sits out and the warp stays converged
 #pragma unroll 2
@@ -1250,10 +1242,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 tmem_get_row<D>(my_taddr + (uint32_t)(jt * 4 * D), xr, sr);
                 update_row(i_cur, slot, xr, sr);
             }
-            j_stream += rpt_tm;
         }
 #pragma unroll 2
-        for (int j = j_stream; j < rpt; ++j, i_cur += TT, slot += nthr) {
+        for (int j = j0_res; j < j0_res + rpt_res; ++j, i_cur += TT, slot += nthr) {
+            const long long i = (j == rpt - 1) ? i_last : i_cur;
+            if (i < a.row_end) {
+                const int rs = slot - j0_res * nthr;
+                T xr[D], sr[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) { xr[k] = xs[k * slots_res + rs]; sr[k] = ss[k * slots_res + rs]; }
+                update_row(i, slot, xr, sr);
+            }
+        }
+#pragma unroll 2
+        for (int j = j0_res + rpt_res; j < rpt; ++j, i_cur += TT, slot += nthr) {
             const long long i = (j == rpt - 1) ? i_last : i_cur;
             if (i < a.row_end) {
                 T xr[D], sr[D];
@@ -1389,20 +1391,13 @@ static int persistent_go2(const ThinArgs<T>& a, const MailArgs& mail, int m, int
     return 1;
 }
 
-// GFK_TMEM=1 (opt-in): park as many full passes of rows as fit in tensor memory (float64, d = 2 or 4)
+// rpt_tm > 0 selects the tensor-memory instantiation (float64, d = 2 or 4 only)
 template <typename T, int D, bool STRICT, bool MULTI, bool WDD>
-static int persistent_go(const ThinArgs<T>& a, const MailArgs& mail, int m, int rpt, int rpt_res, unsigned grid,
-                         int threads, size_t smem, cudaStream_t st) {
+static int persistent_go(const ThinArgs<T>& a, const MailArgs& mail, int m, int rpt, int rpt_res, int rpt_tm,
+                         unsigned grid, int threads, size_t smem, cudaStream_t st) {
     if constexpr (std::is_same<T, double>::value && (D == 2 || D == 4)) {
-        const char* env = getenv("GFK_TMEM");
-        if (env && env[0] == '1' && threads == kPersistThreads) {
-            const int slots = (kTmemCols / 4) / (4 * D);          // 128 columns per warp / columns per row
-            int rpt_tm = rpt - 1 - rpt_res;                       // full passes after the shared-memory ones
-            if (rpt_tm > slots) rpt_tm = slots;
-            if (rpt_tm > 0)
-                return persistent_go2<T, D, STRICT, MULTI, WDD, true>(a, mail, m, rpt, rpt_res, rpt_tm, grid, threads,
-                                                                      smem, st);
-        }
+        if (rpt_tm > 0)
+            return persistent_go2<T, D, STRICT, MULTI, WDD, true>(a, mail, m, rpt, rpt_res, rpt_tm, grid, threads, smem, st);
     }
     return persistent_go2<T, D, STRICT, MULTI, WDD, false>(a, mail, m, rpt, rpt_res, 0, grid, threads, smem, st);
 }
@@ -1427,22 +1422,31 @@ static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, c
     const size_t base = slots * (sizeof(double) + (a.lw ? sizeof(T) : 0));
     const size_t budget = (size_t)smem_optin - 1024;   // minus the kernel's static shared memory
     if (base > budget) return 0;
-    // as many of each thread's rows as fit stay in shared memory for the whole job; the rest stream via L2
+    // Tensor memory first (opt-in GFK_TMEM=1, float64, d = 2 or 4): full passes only - every thread owns a row there.
+    int rpt_tm = 0;
+    if (std::is_same<T, double>::value && (D == 2 || D == 4)) {
+        const char* tenv = getenv("GFK_TMEM");
+        if (tenv && tenv[0] == '1') {
+            rpt_tm = (kTmemCols / 4) / (4 * D);                   // 128 columns per warp / columns per row
+            if (rpt_tm > rpt - 1) rpt_tm = rpt - 1;
+        }
+    }
+    // then as many of the remaining passes as fit stay in shared memory for the whole job; the rest stream via L2
     const size_t per_row_slot = 2 * (size_t)D * threads * sizeof(T);
     int rpt_res = (int)((budget - base) / per_row_slot);
-    if (rpt_res > rpt) rpt_res = rpt;
+    if (rpt_res > rpt - rpt_tm) rpt_res = rpt - rpt_tm;
     const char* env = getenv("GFK_RESIDENT");
     if (env && env[0] == '0') rpt_res = 0;
     const size_t smem = base + (size_t)rpt_res * per_row_slot;
     const unsigned g = (unsigned)grid;
     if constexpr (STRICT) {
         if (a.lw && a.w) {       // double-double exponentials present: weights without the device exp
-            return a.n_ranks > 1 ? persistent_go<T, D, STRICT, true, true>(a, mail, m, rpt, rpt_res, g, threads, smem, st)
-                                 : persistent_go<T, D, STRICT, false, true>(a, mail, m, rpt, rpt_res, g, threads, smem, st);
+            return a.n_ranks > 1 ? persistent_go<T, D, STRICT, true, true>(a, mail, m, rpt, rpt_res, rpt_tm, g, threads, smem, st)
+                                 : persistent_go<T, D, STRICT, false, true>(a, mail, m, rpt, rpt_res, rpt_tm, g, threads, smem, st);
         }
     }
-    return a.n_ranks > 1 ? persistent_go<T, D, STRICT, true, false>(a, mail, m, rpt, rpt_res, g, threads, smem, st)
-                         : persistent_go<T, D, STRICT, false, false>(a, mail, m, rpt, rpt_res, g, threads, smem, st);
+    return a.n_ranks > 1 ? persistent_go<T, D, STRICT, true, false>(a, mail, m, rpt, rpt_res, rpt_tm, g, threads, smem, st)
+                         : persistent_go<T, D, STRICT, false, false>(a, mail, m, rpt, rpt_res, rpt_tm, g, threads, smem, st);
 }
 
 
