@@ -970,11 +970,37 @@ __device__ __forceinline__ void tmem_get_row(uint32_t taddr, double (&x)[D], dou
         sx[k] = __longlong_as_double((long long)(((unsigned long long)r[2 * D + 2 * k + 1] << 32) | r[2 * D + 2 * k]));
     }
 }
-// float rows are never parked in tensor memory (the template flag is only instantiated for float64)
+// float32 rows: 2 D columns; only d = 4 (8 columns, one .x8 access) is instantiated
 template <int D>
-__device__ __forceinline__ void tmem_put_row(uint32_t, const float (&)[D], const float (&)[D]) {}
+__device__ __forceinline__ void tmem_put_row(uint32_t taddr, const float (&x)[D], const float (&sx)[D]) {
+    static_assert(D == 4, "tensor-memory row store (float32): d = 4");
+    uint32_t r[8];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        r[k] = __float_as_uint(x[k]);
+        r[D + k] = __float_as_uint(sx[k]);
+    }
+    tmem_st8(taddr, r);
+}
 template <int D>
-__device__ __forceinline__ void tmem_get_row(uint32_t, float (&)[D], float (&)[D]) {}
+__device__ __forceinline__ void tmem_get_row(uint32_t taddr, float (&x)[D], float (&sx)[D]) {
+    static_assert(D == 4, "tensor-memory row store (float32): d = 4");
+    uint32_t r[8];
+    tmem_ld8(taddr, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        x[k] = __uint_as_float(r[k]);
+        sx[k] = __uint_as_float(r[D + k]);
+    }
+}
+
+// element types / dimensions with a tensor-memory instantiation, and the columns one row takes
+template <typename T, int D>
+struct TmemRow {
+    static constexpr bool ok = (std::is_same<T, double>::value && (D == 2 || D == 4)) || (std::is_same<T, float>::value && D == 4);
+    static constexpr int cols = 2 * D * (int)sizeof(T) / 4;
+};
 
 // ---- all m greedy steps in ONE cooperative launch (single rank, small D) -------------------------------
 // One CTA per SM (or fewer for small shards).  Thread g of the grid owns rows g, g + T, g + 2T, ... for the
@@ -1080,7 +1106,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
             T xr[D], sr[D];
             load_row<D>(a.x, i, xr);
             load_row<D>(a.s, i, sr);
-            tmem_put_row<D>(my_taddr + (uint32_t)(jt * 4 * D), xr, sr);
+            tmem_put_row<D>(my_taddr + (uint32_t)(jt * TmemRow<T, D>::cols), xr, sr);
         }
         tmem_wait_st();
     }
@@ -1239,7 +1265,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
 #pragma unroll 2
             for (int jt = 0; jt < rpt_tm; ++jt, i_cur += TT, slot += nthr) {
                 T xr[D], sr[D];
-                tmem_get_row<D>(my_taddr + (uint32_t)(jt * 4 * D), xr, sr);
+                tmem_get_row<D>(my_taddr + (uint32_t)(jt * TmemRow<T, D>::cols), xr, sr);
                 update_row(i_cur, slot, xr, sr);
             }
         }
@@ -1395,7 +1421,7 @@ static int persistent_go2(const ThinArgs<T>& a, const MailArgs& mail, int m, int
 template <typename T, int D, bool STRICT, bool MULTI, bool WDD>
 static int persistent_go(const ThinArgs<T>& a, const MailArgs& mail, int m, int rpt, int rpt_res, int rpt_tm,
                          unsigned grid, int threads, size_t smem, cudaStream_t st) {
-    if constexpr (std::is_same<T, double>::value && (D == 2 || D == 4)) {
+    if constexpr (TmemRow<T, D>::ok) {
         if (rpt_tm > 0)
             return persistent_go2<T, D, STRICT, MULTI, WDD, true>(a, mail, m, rpt, rpt_res, rpt_tm, grid, threads, smem, st);
     }
@@ -1422,12 +1448,12 @@ static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, c
     const size_t base = slots * (sizeof(double) + (a.lw ? sizeof(T) : 0));
     const size_t budget = (size_t)smem_optin - 1024;   // minus the kernel's static shared memory
     if (base > budget) return 0;
-    // Tensor memory first (opt-in GFK_TMEM=1, float64, d = 2 or 4): full passes only - every thread owns a row there.
+    // Tensor memory first (opt-in GFK_TMEM=1; float64 d = 2 or 4, float32 d = 4): full passes only - every thread owns a row there.
     int rpt_tm = 0;
-    if (std::is_same<T, double>::value && (D == 2 || D == 4)) {
+    if (TmemRow<T, D>::ok) {
         const char* tenv = getenv("GFK_TMEM");
         if (tenv && tenv[0] == '1') {
-            rpt_tm = (kTmemCols / 4) / (4 * D);                   // 128 columns per warp / columns per row
+            rpt_tm = (kTmemCols / 4) / TmemRow<T, D>::cols;       // 128 columns per warp / columns per row
             if (rpt_tm > rpt - 1) rpt_tm = rpt - 1;
         }
     }

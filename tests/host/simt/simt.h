@@ -113,6 +113,8 @@ inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 inline int __double2hiint(double d) { long long v; memcpy(&v, &d, 8); return (int)(v >> 32); }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline double rsqrt(double a) { return 1.0 / sqrt(a); }
 inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 

@@ -668,7 +668,7 @@ def test_tensor_memory_row_store_equals_the_default_kernel(d, monkeypatch):
     log_q = log_p + 0.5 * np.sin(x[:, 0])
     m = 6
     expect = ot.thin_gf(x, log_p, log_q, g, m, preconditioner='med')
-    for precision in ('f64', 'f64-fast'):
+    for precision in ('f64', 'f64-fast') + (('f32',) if d == 4 else ()):
         monkeypatch.delenv('GFK_TMEM', raising=False)
         base = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(m)
         monkeypatch.setenv('GFK_TMEM', '1')
@@ -682,9 +682,10 @@ def test_tensor_memory_row_store_equals_the_default_kernel(d, monkeypatch):
             # (passes in tensor memory) x 1024 threads: one store each, one load per greedy update; of the 12 passes
             # the 11 full ones qualify: 8 fit at d = 4 (16 columns per row), all 11 at d = 2
             passes, rem = divmod(lib.simt_tmem_access_count() - before, 1024 * m)
-            assert rem == 0 and passes == (8 if d == 4 else 11)
+            assert rem == 0 and passes == (11 if (d == 2 or precision == 'f32') else 8)
         H.set_schedule(False)
-        assert np.array_equal(base[0], expect), precision
+        if precision != 'f32':
+            assert np.array_equal(base[0], expect), precision
     # score-based kernel and a shard that fits shared memory entirely (no tensor-memory pass: falls back silently)
     monkeypatch.setenv('GFK_TMEM', '1')
     assert np.array_equal(H.SimProblem(x, g, preconditioner='med').thin(m)[0], ot.thin(x, g, m, preconditioner='med'))
