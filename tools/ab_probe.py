@@ -10,7 +10,7 @@ warnings.simplefilter('ignore')
 tag = os.environ.get('AB_TAG', 'head')
 for cname in ('c1', 'c2', 'c3'):
     c = synthetic.CONFIGS[cname]()
-    for prec in ('f64', 'f64-fast'):
+    for prec in ('f64', 'f64-fast', 'f32'):
         if c['kind'] == 'gf':
             p = SteinProblem(c['sample'], c['gradient_q'], log_p=c['log_p'], log_q=c['log_q'], preconditioner='med', precision=prec)
         else:
