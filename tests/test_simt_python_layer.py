@@ -218,3 +218,12 @@ def test_product_still_refuses_to_run_without_cuda():
     from gradient_free_mcmc_postprocessing_b200 import _engine
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         _engine._require_cuda(None)
+
+
+def test_driver_smoke_entry_runs_over_the_emulator(api, monkeypatch, capsys):
+    """__graft_entry__.smoke() is GPU-only; its Python (fixture names, API calls, tolerances) is checked here by
+    running it over the emulator build - the CUDA availability assertion is the only thing patched away."""
+    import __graft_entry__ as entry
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
+    entry.smoke()
+    assert 'smoke ok' in capsys.readouterr().out
