@@ -8,6 +8,8 @@ mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/smi.log 2>&1
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q -rxX > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/pytest_gpu.log
 echo "== smoke"; timeout 200 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/smoke.log
+echo "== compute-sanitizer memcheck on the small smoke job (misaligned / out-of-bounds accesses are reported with their source line)"
+timeout 400 compute-sanitizer --tool memcheck --print-limit 20 python __graft_entry__.py smoke > gpurun_out/memcheck_smoke.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/memcheck_smoke.log
 echo "== bench"; timeout 400 python bench.py > gpurun_out/bench_n1.log 2> gpurun_out/bench_n1.err; echo "rc=$?"; head -c 600 gpurun_out/bench_n1.log
 echo "== bench reference arm"; timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; echo "rc=$?"
 echo "== probes"; timeout 400 python tools/gpu_probe.py > gpurun_out/probe.log 2>&1; echo "rc=$?"
