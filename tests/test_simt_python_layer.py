@@ -227,3 +227,31 @@ def test_driver_smoke_entry_runs_over_the_emulator(api, monkeypatch, capsys):
     monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
     entry.smoke()
     assert 'smoke ok' in capsys.readouterr().out
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_public_api_under_a_process_group(world):
+    """`distributed.init()` + thin / thin_gf / ksd as called under torchrun, on `world` emulated ranks (gloo for the
+    plumbing, fake NCCL + emulated cudaIpc for the library): every rank returns the oracle's sequence, through the
+    peer mailboxes (single-launch and launch-per-step kernels) and through the all-gather fallback."""
+    import socket
+    import subprocess
+    import sys
+    H.load()
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = str(s.getsockname()[1])
+    import os
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'simt_dist_worker.py')
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=600)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and 'SIMT_DIST_OK %d %d' % (r, world) in out, out[-3000:]
