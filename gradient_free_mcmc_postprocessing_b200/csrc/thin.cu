@@ -1013,7 +1013,9 @@ struct TmemRow {
 constexpr int kPersistThreads = 512;
 constexpr int kPollPerLane = 5;                       // persistent grid <= 160 CTAs (one per SM)
 
-// WDD (strict mode only): gradient-free weights from the per-row double-double exponentials in a.w (exp_sum_dd)
+// WDD: a.w is present - strict mode: per-row double-double exponentials (exp_sum_dd); fast modes: plain exp(lw), the
+// weight is a product.  Without it the weight is exp(lw_i + lw_y) per pair; as a template flag so that the loop of
+// either variant does not carry the other's code.
 // TM: passes [0, rpt_tm) of every thread's rows are parked in tensor memory (float64, d = 2 or 4), the next rpt_res
 // passes in shared memory, the rest streams through L2
 template <typename T, int D, bool STRICT, bool MULTI, bool WDD, bool TM>
@@ -1043,7 +1045,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     const int j0_res = TM ? rpt_tm : 0;                          // passes [0, rpt_tm): tensor memory; then shared memory
     T* xs = lw_sh + (a.lw ? slots : 0);                          // resident x as [D][slots_res], then s
     T* ss = xs + (size_t)D * slots_res;
-    const bool use_w = (!STRICT && a.w != nullptr);
+    constexpr bool use_w = !STRICT && WDD;                       // fast modes: weight = w_i w_y (no exp code in the loop)
     ThinWs* ws = a.ws;
     if (tid == 0) abort_sh = 0;
     __shared__ uint32_t tmem_base_sh;
@@ -1085,7 +1087,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 } else {
                     lw_sh[slot] = lwi;
                     double wgt;
-                    if constexpr (WDD) {
+                    if constexpr (STRICT && WDD) {
                         const double2 e = __ldg(reinterpret_cast<const double2*>(a.w) + i);
                         wgt = exp_sum_dd((double)lwi, (double)lwi, e.x, e.y, e.x, e.y);
                     } else {
@@ -1215,7 +1217,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         T lwy = T(0);
         if (a.lw) lwy = use_w ? __ldg(a.w + sel) : __ldg(a.lw + sel);
         double ehy = 0.0, ely = 0.0;
-        if constexpr (WDD) {
+        if constexpr (STRICT && WDD) {
             if (a.lw) {
                 const double2 e = __ldg(reinterpret_cast<const double2*>(a.w) + sel);
                 ehy = e.x;
@@ -1228,7 +1230,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         // one row of the update: kernel value against y, weight, running objective, in-order argmin
         auto update_row = [&](long long i, int slot, const T (&xr)[D], const T (&sr)[D]) {
             double2 ei = make_double2(0.0, 0.0);
-            if constexpr (WDD) {
+            if constexpr (STRICT && WDD) {
                 if (a.lw) ei = __ldg(reinterpret_cast<const double2*>(a.w) + i);   // in flight under the pair kernel
             }
             double k;
@@ -1239,7 +1241,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
             if constexpr (STRICT) {
                 if (a.lw) {
                     double wgt;
-                    if constexpr (WDD) wgt = exp_sum_dd((double)lw_sh[slot], (double)lwy, ei.x, ei.y, ehy, ely);
+                    if constexpr (STRICT && WDD) wgt = exp_sum_dd((double)lw_sh[slot], (double)lwy, ei.x, ei.y, ehy, ely);
                     else wgt = exp((double)lw_sh[slot] + (double)lwy);
                     k = __dmul_rn(wgt, k);
                 }
@@ -1465,8 +1467,8 @@ static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, c
     if (env && env[0] == '0') rpt_res = 0;
     const size_t smem = base + (size_t)rpt_res * per_row_slot;
     const unsigned g = (unsigned)grid;
-    if constexpr (STRICT) {
-        if (a.lw && a.w) {       // double-double exponentials present: weights without the device exp
+    {
+        if (a.lw && a.w) {       // pre-exponentiated weights present: no device exp in the loop
             return a.n_ranks > 1 ? persistent_go<T, D, STRICT, true, true>(a, mail, m, rpt, rpt_res, rpt_tm, g, threads, smem, st)
                                  : persistent_go<T, D, STRICT, false, true>(a, mail, m, rpt, rpt_res, rpt_tm, g, threads, smem, st);
         }
