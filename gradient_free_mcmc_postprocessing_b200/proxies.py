@@ -159,3 +159,18 @@ def energy_distance(x, y, *, device=None):
 def fit_quality(validation_sample, subsample, validation_sample_step=10, *, device=None):
     """``Comparison.ipynb#c19`` with the validation sample passed explicitly."""
     return float(np.sqrt(energy_distance(validation_sample[::validation_sample_step], subsample, device=device)))
+
+
+def energy_distance_curve(validation_sample, sample, idx, thinned_sizes, validation_sample_step=10, *, device=None):
+    """``rw_energy_distance`` of ``Comparison.ipynb#c21-#c22``: rows ``[thinned_size, fit_quality(sample[idx[:size]])]``
+    for every requested size - from ONE cumulative pass instead of one energy-distance evaluation per size."""
+    idx = np.asarray(idx).astype(np.int64)
+    sizes = np.asarray(thinned_sizes, dtype=np.int64)
+    if sizes.size and (sizes.min() < 1 or sizes.max() > idx.shape[0]):
+        raise ValueError('thinned sizes must lie in [1, len(idx)]')
+    if isinstance(sample, torch.Tensor):
+        selected = sample[torch.as_tensor(idx, device=sample.device)]
+    else:
+        selected = np.asarray(sample)[idx]
+    e2 = cumulative_energy_distance(validation_sample[::validation_sample_step], selected, device=device)
+    return np.stack([sizes.astype(float), np.sqrt(np.maximum(e2[sizes - 1], 0.0))], axis=1)

@@ -193,6 +193,14 @@ def test_next_rows_through_the_public_api(api, g13, g45, tmp_path):
     assert abs(p.fit_quality(xv, yv, 10) - nr.fit_quality(xv, yv, 10)) < 1e-12
     with pytest.raises(ValueError):
         p.cumulative_energy_distance(xv, yv[:, :2])
+    sel = rng.integers(0, 700, 60)
+    sizes = np.array([5, 17, 60])
+    curve = p.energy_distance_curve(xv, xv, sel, sizes, validation_sample_step=7)      # Comparison.ipynb#c22
+    assert curve.shape == (3, 2) and np.array_equal(curve[:, 0], sizes)
+    for size, val in curve:
+        assert abs(val - nr.fit_quality(xv, xv[sel[:int(size)]], 7)) < 1e-11
+    with pytest.raises(ValueError):
+        p.energy_distance_curve(xv, xv, sel, [0, 3])
     # chains + .npy layer
     paths = []
     for i in range(3):
