@@ -16,8 +16,9 @@ STRATEGY_ENVS = [{}, {'GFK_RESIDENT': '0'}, {'GFK_PERSISTENT': '0'}]
 @settings(max_examples=int(os.environ.get('GFK_FUZZ_EXAMPLES', '40')), derandomize='GFK_FUZZ_EXAMPLES' not in os.environ, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(2, 1400), d=st.integers(1, 12), m=st.integers(1, 24),
        dup=st.sampled_from([0.0, 0.3, 0.8]), pre=st.sampled_from(['id', 'med', 'sclmed', '0.7']), gf=st.booleans(),
-       strategy=st.integers(0, 2), sms=st.integers(1, 6), fast=st.booleans(), scale=st.sampled_from([1e-3, 1.0, 50.0]))
-def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fast, scale):
+       strategy=st.integers(0, 2), sms=st.integers(1, 6), fast=st.booleans(), scale=st.sampled_from([1e-3, 1.0, 50.0]),
+       tmem=st.booleans())
+def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fast, scale, tmem):
     rng = np.random.default_rng(seed)
     base = rng.standard_normal((n, d)) * scale + rng.standard_normal(d)
     keep = rng.random(n) > dup
@@ -32,6 +33,7 @@ def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fas
         os.environ.pop(k, None)
     os.environ.update(STRATEGY_ENVS[strategy])
     os.environ['SIMT_SMS'] = str(sms)
+    os.environ['GFK_TMEM'] = '1' if tmem else '0'          # opt-in tensor-memory row store (d = 2, 4 only)
     H.set_schedule(False)
     precision = 'f64-fast' if fast else 'f64'
     try:
@@ -68,7 +70,7 @@ def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fas
                    else ot._make_stein_integrand(x, g, preconditioner=pre))
             np.testing.assert_allclose(p.ksd(), os_.ksd(ref, n), rtol=1e-10)
     finally:
-        for k in ('GFK_PERSISTENT', 'GFK_RESIDENT', 'SIMT_SMS'):
+        for k in ('GFK_PERSISTENT', 'GFK_RESIDENT', 'SIMT_SMS', 'GFK_TMEM'):
             os.environ.pop(k, None)
 
 
