@@ -70,17 +70,23 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 #endif
 
-// stage dimensions [k0, k0 + kc) of rows [t0, t0 + TILE) into dst[k][LD] (zero padded), asynchronously.
-// Consecutive threads read consecutive k of one row (coalesced); the padded LD spreads the stores.
+// stage dimensions [k0, k0 + kc) of rows [t0, t0 + TILE) into dst[k][LD] (rows beyond m zeroed), asynchronously.
+// Consecutive threads read consecutive k of one row (coalesced); the padded LD spreads the stores.  Only the kc
+// dimensions the consumer reads are touched (at d = 10 that is 10 of the chunk's 32 rows of dst: a third of the
+// staging work of a full chunk); (r, k) advance incrementally - one division per call, none per element.
 template <typename T, int KC>
 __device__ __forceinline__ void stage_tile(const KsdArgs<T>& a, const T* __restrict__ src, long long t0, int k0,
                                            int kc, T* __restrict__ dst) {
     const int d = a.kp.d;
-    for (int e = threadIdx.x; e < TILE * KC; e += KSD_THREADS) {
-        const int r = e / KC, k = e - r * KC;
+    int r = (int)threadIdx.x / kc, k = (int)threadIdx.x - r * kc;
+    const int dr = KSD_THREADS / kc, dk = KSD_THREADS - dr * kc;
+    for (int e = threadIdx.x; e < TILE * kc; e += KSD_THREADS) {
         const long long t = t0 + r;
-        if (k < kc && t < a.m) cp_async_elem(dst + k * LD + r, src + row_of(a, t) * d + k0 + k);
+        if (t < a.m) cp_async_elem(dst + k * LD + r, src + row_of(a, t) * d + k0 + k);
         else dst[k * LD + r] = T(0);
+        r += dr;
+        k += dk;
+        if (k >= kc) { k -= kc; ++r; }
     }
 }
 
