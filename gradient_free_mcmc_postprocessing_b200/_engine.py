@@ -247,8 +247,7 @@ class SteinProblem:
             # operations, is correctly rounded and machine independent (csrc/stein_math.cuh exp_sum_dd) - unless a
             # log-weight is so large that exp(lw_i) alone could overflow or go subnormal; then the device exp stays
             rng = (ctypes.c_double * 2)()
-            ws = _bytes(lib.gfk_log_weights_ws_bytes(), self.device)
-            check(lib.gfk_log_weights_range(_ptr(klw), self.n, rng, _ptr(ws), st))
+            check(lib.gfk_log_weights_last_range(rng))         # host statistics of the gfk_log_weights call above
             self.lw_range = (rng[0], rng[1])
             # GFK_EXP_DD=0: keep the device exp (A/B measurements only)
             if -EXP_DD_LIMIT <= rng[0] and rng[1] <= EXP_DD_LIMIT and os.environ.get('GFK_EXP_DD', '1') != '0':

@@ -53,6 +53,7 @@ PROTOTYPES = {
     'gfk_log_weights': (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _dbl, _vp, _pd, _vp, _vp]),
     'gfk_exp_weights': (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _vp]),
     'gfk_exp_weights_dd': (ctypes.c_int, [_vp, _vp, _i64, _vp]),
+    'gfk_log_weights_last_range': (ctypes.c_int, [_pd]),
     'gfk_log_weights_range': (ctypes.c_int, [_vp, _i64, _pd, _vp, _vp]),
     'gfk_gaussian_proxy': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _dbl, _vp, _vp, _vp]),
     'gfk_student_t_proxy': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _dbl, _dbl, _vp, _vp, _vp]),

@@ -431,6 +431,18 @@ extern "C" int gfk_exp_weights_dd(const double* lw, double* ew, int64_t count, v
     return GFK_OK;
 }
 
+// range of the log-weights written by this thread's most recent gfk_log_weights call (host bookkeeping only)
+static thread_local double g_last_lw_min = 0.0, g_last_lw_max = 0.0;
+static thread_local bool g_last_lw_valid = false;
+
+extern "C" int gfk_log_weights_last_range(double* min_max_host) {
+    GFK_REQUIRE(min_max_host, "gfk_log_weights_last_range: NULL output");
+    GFK_REQUIRE(g_last_lw_valid, "gfk_log_weights_last_range: no gfk_log_weights call on this thread yet");
+    min_max_host[0] = g_last_lw_min;
+    min_max_host[1] = g_last_lw_max;
+    return GFK_OK;
+}
+
 extern "C" size_t gfk_log_weights_ws_bytes(void) { return sizeof(double) * 3 * 1024; }
 
 extern "C" int gfk_log_weights(const double* log_p, const double* log_q, int64_t n, int use_cap, double range_cap,
@@ -456,6 +468,10 @@ extern "C" int gfk_log_weights(const double* log_p, const double* log_q, int64_t
         return GFK_ENUMERIC;
     }
     *spread_host = mx - mn;
+    // what lw_apply_kernel is about to write: lw itself, or max(lw - mx, -cap) (monotone, so the extremes map to extremes)
+    g_last_lw_min = use_cap ? fmax(mn - mx, -range_cap) : mn;
+    g_last_lw_max = use_cap ? fmax(0.0, -range_cap) : mx;
+    g_last_lw_valid = true;
     lw_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(log_p, log_q, n, use_cap, mx, range_cap, lw);
     count_launches(2);
     GFK_CHECK_LAUNCH();

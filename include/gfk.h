@@ -122,6 +122,9 @@ int gfk_exp_weights_dd(const double* lw, double* ew, int64_t count, void* stream
  * pre-exponentiated weights (one multiplication per pair instead of one exp) whenever every |lw| is far from the
  * overflow / underflow range of exp; the caller decides with this.  ws: gfk_log_weights_ws_bytes(). */
 int gfk_log_weights_range(const double* lw, int64_t n, double* min_max_host, void* ws, void* stream);
+/* the same two numbers for the lw written by this thread's most recent gfk_log_weights call, from its own host-side
+ * statistics: no launch, no synchronisation */
+int gfk_log_weights_last_range(double* min_max_host);
 
 /* ---- next: the Gaussian proxy of gaussian_thin, code/src/thinning.py:15-16 ----------------
  * log_q[i] = -0.5 (cst + (x_i - mean)' P (x_i - mean)) with cst = d log(2 pi) + log det(cov) (what scipy's

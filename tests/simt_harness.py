@@ -176,8 +176,11 @@ class SimProblem:
             check(lib.gfk_exp_weights(ptr(klw), ptr(self.w), n, int(self.mode == F32_FAST), None))
         elif klw is not None:                  # strict mode: double-double exponentials when the range allows
             rng = (ctypes.c_double * 2)()
+            check(lib.gfk_log_weights_last_range(rng))
+            rng2 = (ctypes.c_double * 2)()                     # the kernel-computed range must agree
             rws = guarded((lib.gfk_log_weights_ws_bytes(),), np.uint8)
-            check(lib.gfk_log_weights_range(ptr(klw), n, rng, ptr(rws), None))
+            check(lib.gfk_log_weights_range(ptr(klw), n, rng2, ptr(rws), None))
+            assert (rng[0], rng[1]) == (rng2[0], rng2[1]), ((rng[0], rng[1]), (rng2[0], rng2[1]))
             self.lw_range = (rng[0], rng[1])
             if -350.0 <= rng[0] and rng[1] <= 350.0 and os.environ.get('GFK_TEST_NO_EXP_DD') != '1':
                 self.w = guarded((n, 2), np.float64, fill=np.nan)
