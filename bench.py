@@ -20,6 +20,8 @@ n = 10^6 in total (the literal C3-on-8-GPUs case, also reported under "strong" i
 `roofline`: the thinning kernel - algorithmic bytes (16d + 16 + 8 per candidate row per greedy step,
             SURVEY.md section 8d) / time per greedy step (CUDA events around the kernel(s) of one job,
             divided by m), against the measured HBM peak in MEASURED_PEAKS.json
+`thin_c2`, `ksd_c4` (N = 1 only): secondary numbers measured in a subprocess after the headline - the C2 job
+            (score-based, n = 2 x 10^5) and the full C4 KSD (n = 2 x 10^5, d = 10) with its FP64 roofline fraction
 `cpu_baseline`: the numpy oracle (restatement of the reference's stein_thinning path) timed on this
             host on a bounded sample of the same workload (same n, reduced m)
 """
