@@ -218,13 +218,27 @@ class SteinProblem:
             self.lam = float(linv[0, 0])
             self.lam_sq = float(np.dot(linv, linv)[0, 0])
         else:
-            # dense symmetric L: the kernels use xl = x @ L and unit lambda (stein_math.cuh)
-            sym = 0.5 * (dense + dense.T)
+            # dense L: the kernels use xl = x @ L and unit lambda (stein_math.cuh), which equals the reference's
+            # x' L L x / (L ds)' x terms only for a SYMMETRIC L - anything else is refused, not symmetrised
+            asym = float(np.max(np.abs(dense - dense.T)))
+            if asym > 1e-12 * float(np.max(np.abs(dense))):
+                raise ValueError('a dense linv must be symmetric (max |L - L^T| = %.3g): the reference evaluates '
+                                 "x' L L x with L as given, which the device formulation reproduces only for "
+                                 'symmetric L' % asym)
+            sym = 0.5 * (dense + dense.T)          # removes rounding-level asymmetry only
             self.xl = self.x @ torch.from_numpy(sym).to(self.device)
             self.lam = self.lam_sq = 1.0
             if self.mode == _lib.F64_STRICT:
-                self.mode = _lib.F64_FAST   # numpy's BLAS summation order is not reproducible
+                # numpy's BLAS summation order for np.dot(linv, .) is not reproducible: no strict formulation exists
+                self.mode = _lib.F64_FAST
+                warnings.warn("a dense preconditioner runs in the 'f64-fast' formulation (FMA sums); the strict "
+                              "'f64' parity mode covers scalar preconditioners ('id', 'med', 'sclmed', numeric) only")
         self.trace = float(np.trace(linv))
+
+    @property
+    def precision(self):
+        """The arithmetic mode the kernels actually run in ('f64' may have become 'f64-fast', see above)."""
+        return {_lib.F64_STRICT: 'f64', _lib.F64_FAST: 'f64-fast', _lib.F32_FAST: 'f32'}[self.mode]
 
     def _finalise_dtype(self):
         """Build the arrays the kernels read: float32 copies for f32, exp(lw) for the fast modes."""

@@ -173,6 +173,16 @@ extern "C" int gfk_p2p_open(const void* handles_host, int n_ranks, int rank) {
 
 extern "C" int gfk_p2p_enabled(void) { return g_mail_open ? 1 : 0; }
 
+#if defined(GFK_SIMT_HOST)
+// emulator build of the test suite only: this rank's mailbox and the tag base / parity the NEXT job will use, so a
+// test can plant a forged or stale record (tests/test_simt_fault_protocol.py)
+extern "C" unsigned long long* gfk_test_mailbox(unsigned* next_tag_base, int* next_job_parity) {
+    if (next_tag_base) *next_tag_base = g_tag_epoch;
+    if (next_job_parity) *next_job_parity = (int)(g_job_count & 1u);
+    return g_mail_local;
+}
+#endif
+
 extern "C" int gfk_comm_finalize(void) {
     if (g_mail_open) {
         for (int r = 0; r < kMailRanks; ++r) {

@@ -14,7 +14,11 @@ int comm_allgather16(const void* send, void* recv, cudaStream_t st);
 // sees the expected tag in the three payload words of a slot has the whole record: no fences, no atomics,
 // one NVLink store latency per step instead of an NCCL launch.
 constexpr int kMailRanks = 16;
-constexpr int kMailWords = 2 * 2 * kMailRanks * 4;
+constexpr int kMailSlotWords = 2 * 2 * kMailRanks * 4;
+// one extra 128-byte line after the slots: word kMailPoison holds the tag_base of a job that a peer aborted
+// (written by that peer into every mailbox; polled by every wait of the job, see thin.cu "failure protocol")
+constexpr int kMailPoison = kMailSlotWords;
+constexpr int kMailWords = kMailSlotWords + 16;
 struct MailArgs {
     unsigned long long* local;             // this rank's mailbox (peers write into it)
     unsigned long long* peer[kMailRanks];  // every rank's mailbox as mapped in this process (peer[rank] == local)

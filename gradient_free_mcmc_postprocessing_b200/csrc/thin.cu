@@ -31,8 +31,10 @@ struct __align__(16) ThinWs {
     Cand partial[kMaxBlocks];
     unsigned counter;        // last-block-done ticket / persistent-kernel barrier arrivals
     unsigned step;           // greedy step whose winner is in recv[]
-    unsigned abort;          // persistent kernel: a barrier spin ran out (never expected)
+    unsigned abort;          // kAbort*: an exchange timed out / a peer aborted / an exchanged index was out of range
     unsigned pad_;
+    unsigned long long spin_ns;        // deadline of every wait on another CTA / rank (GFK_SPIN_MS, default 200 ms)
+    unsigned long long spin_first_ns;  // ... of the first cross-rank exchange of a job (GFK_SPIN_FIRST_MS): host skew
     // persistent kernel, flag-in-data slots: every 8-byte word carries (tag << 32 | payload), so a reader
     // that sees the expected tag in all three words has the whole record - no fences, no atomics
     __align__(16) unsigned long long ll[2][kMaxBlocks / 2][4];
@@ -46,6 +48,7 @@ struct __align__(16) ThinWs {
 
 static_assert(offsetof(ThinWs, ll) % 16 == 0 && offsetof(ThinWs, bcast) % 16 == 0 && sizeof(ThinWs::ll[0][0]) == 32,
               "flag-in-data slots are moved with 16-byte vector accesses");
+static_assert(offsetof(ThinWs, spin_ns) % 8 == 0, "64-bit fields are naturally aligned");
 static_assert(offsetof(ThinWs, send) % 16 == 0 && offsetof(ThinWs, recv) % 16 == 0, "Cand records are 16-byte aligned");
 
 #ifdef GFK_TRACE
@@ -74,6 +77,7 @@ struct ThinArgs {
     const T* xl;    // x @ L for a dense preconditioner (nullptr: scalar)
     double* A;
     long long row_begin, row_end;
+    long long n;     // rows of the replica: every exchanged index is checked against it before it is used as an address
     KParams kp;
     ThinWs* ws;
     uint32_t* idx_out;
@@ -133,11 +137,43 @@ struct View {
     __device__ __forceinline__ T operator[](int k) const { return p[k]; }
 };
 
-constexpr unsigned kSpinLimit = 1u << 27;
+// ---- failure protocol ---------------------------------------------------------------------------------------
+// Every wait on memory that another CTA or another rank writes is bounded by a TIME deadline (globaltimer), never
+// by an iteration count: a polling round is an L2 or NVLink round trip of unknown length.  When a wait runs out
+// the waiter sets ws->abort (all local CTAs poll it in their own waits and leave), and - multi-rank - stores this
+// job's tag into the poison word of every peer mailbox, which the peers' waits poll as well, so every rank leaves
+// within one deadline.  A record that does arrive is still range-checked before its index is used as an address.
+// gfk_thin_check() reports the abort code as GFK_ECUDA.
+constexpr unsigned kAbortTimeout = 1u;     // a wait ran out
+constexpr unsigned kAbortPeer = 2u;        // a peer rank posted its poison word
+constexpr unsigned kAbortIndex = 3u;       // an exchanged index was >= n
+constexpr unsigned kSpinCheckEvery = 64u;  // read the timer every 64th unsuccessful polling round only
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     return *reinterpret_cast<const volatile unsigned*>(p);
 }
+
+__device__ __forceinline__ unsigned long long gfk_timer_ns() {
+#if defined(GFK_SIMT_HOST)
+    return simt::now_ns();
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+    return t;
+#endif
+}
+
+// one per wait loop; expired() is called after every unsuccessful polling round
+struct SpinDeadline {
+    unsigned rounds = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ bool expired(unsigned long long limit_ns) {
+        if ((++rounds % kSpinCheckEvery) != 0) return false;
+        const unsigned long long now = gfk_timer_ns();
+        if (t0 == 0) { t0 = now; return false; }
+        return now - t0 > limit_ns;
+    }
+};
 
 // inside every spin loop on memory another CTA / rank writes: nothing on the device; the CPU emulation build of
 // the test suite (tests/host/simt) lets the other emulated threads run
@@ -199,64 +235,106 @@ __device__ __forceinline__ void mail_post(const MailArgs& m, int n_ranks, int ex
     }
 }
 
+// lanes 0 .. n_ranks-1 of one warp: tell every rank (this one included) that this job is over
+__device__ __forceinline__ void mail_poison(const MailArgs& m, int n_ranks, int lane) {
+    if (lane < n_ranks) {
+        volatile unsigned long long* w = m.peer[lane] + kMailPoison;
+        *w = (unsigned long long)m.tag_base;
+    }
+}
+__device__ __forceinline__ bool mail_poisoned(const MailArgs& m) {
+    const volatile unsigned long long* w = m.local + kMailPoison;
+    return *w == (unsigned long long)m.tag_base;
+}
+
 // a full warp: lane r polls slot r of the local mailbox until its three tags match, then the warp reduces
-// the candidates with numpy.argmin semantics.  Every lane returns the winner.  dead: a spin ran out.
-__device__ __forceinline__ Cand mail_wait(const MailArgs& m, int n_ranks, int exchange, int lane, bool& dead,
-                                          const unsigned* abort_flag) {
+// the candidates with numpy.argmin semantics.  Every lane returns the winner.  dead != 0 (a kAbort* code, the same
+// in every lane): the wait ran out, the local abort flag went up or a peer posted its poison word - the returned
+// record is then (+inf, 0xffffffff), never a stale slot.
+__device__ __forceinline__ Cand mail_wait(const MailArgs& m, int n_ranks, int exchange, int lane, unsigned& dead,
+                                          const unsigned* abort_flag, unsigned long long limit_ns) {
     double v = __longlong_as_double(0x7ff0000000000000LL);
     unsigned i = 0xffffffffu;
-    bool bad = false;
+    unsigned bad = 0;
     if (lane < n_ranks) {
         const unsigned tag = m.tag_base + (unsigned)exchange + 1u;
         const volatile unsigned long long* w = m.local + mail_offset(m, exchange, lane);
         unsigned long long w0, w1, w2;
-        unsigned spins = 0;
+        SpinDeadline dl;
 #pragma unroll 1
         for (;;) {
             w0 = w[0]; w1 = w[1]; w2 = w[2];
             if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && (unsigned)(w2 >> 32) == tag) break;
-            if (++spins > kSpinLimit || (abort_flag && ld_volatile_u32(abort_flag))) { bad = true; break; }
+            if (abort_flag && ld_volatile_u32(abort_flag)) { bad = kAbortTimeout; break; }
+            if (mail_poisoned(m)) { bad = kAbortPeer; break; }
+            if (dl.expired(limit_ns)) { bad = kAbortTimeout; break; }
             GFK_SPIN_HINT();
         }
-        v = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
-        i = (unsigned)(w2 & 0xffffffffull);
+        if (!bad) {
+            v = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+            i = (unsigned)(w2 & 0xffffffffull);
+        }
     }
-    dead = __any_sync(0xffffffffu, bad);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned o = __shfl_xor_sync(0xffffffffu, bad, off);
+        bad = o > bad ? o : bad;
+    }
+    dead = bad;
     warp_argmin(v, i);
     Cand c;
-    c.v = v;
-    c.i = i;
+    c.v = dead ? __longlong_as_double(0x7ff0000000000000LL) : v;
+    c.i = dead ? 0xffffffffu : i;
     return c;
 }
 
 // post + wait as one out-of-line call: keeps the single-GPU step loop of the persistent kernel small enough
 // for the instruction cache (one warp walks this code once per step, so every cold line is exposed latency)
 __device__ __noinline__ Cand mail_exchange(const MailArgs& m, int n_ranks, int exchange, double v, unsigned i,
-                                            int lane, bool post, bool& dead, const unsigned* abort_flag) {
+                                            int lane, bool post, unsigned& dead, const unsigned* abort_flag,
+                                            unsigned long long limit_ns) {
     if (post) mail_post(m, n_ranks, exchange, v, i, lane);
-    return mail_wait(m, n_ranks, exchange, lane, dead, abort_flag);
+    return mail_wait(m, n_ranks, exchange, lane, dead, abort_flag, limit_ns);
 }
 
-// winner of exchange (a.step - 1): from the peer mailboxes (warp 0 polls, block broadcast) or from recv[]
+// winner of exchange (a.step - 1): from the peer mailboxes or from recv[]; warp 0 decides, the block gets it through
+// shared memory.  Returns index 0xffffffff when the job is over - aborted by an earlier launch, another CTA or a peer,
+// the exchange timed out, or the record is out of range (then ws->abort goes up and, with mailboxes, the peers are
+// told).  The callers leave at once (winner_ok), so a stale or foreign record never becomes an address.
 template <typename T>
 __device__ __forceinline__ Cand pick_winner(const ThinArgs<T>& a) {
-    if (a.mail_enabled && a.n_ranks > 1) {
-        __shared__ Cand win_bc;
-        if (threadIdx.x < 32) {
-            bool dead;
-            const Cand c = mail_wait(a.ws->mail, a.n_ranks, a.step - 1, threadIdx.x, dead, nullptr);
-            if (threadIdx.x == 0) win_bc = c;
+    __shared__ Cand win_bc;
+    if (threadIdx.x < 32) {
+        const bool mail = a.mail_enabled && a.n_ranks > 1;
+        unsigned dead = __shfl_sync(0xffffffffu, ld_volatile_u32(&a.ws->abort), 0);
+        Cand c;
+        c.v = __longlong_as_double(0x7ff0000000000000LL);
+        c.i = 0xffffffffull;
+        if (!dead) {
+            if (mail) {
+                const unsigned long long limit = (a.step <= 1) ? a.ws->spin_first_ns : a.ws->spin_ns;
+                c = mail_wait(a.ws->mail, a.n_ranks, a.step - 1, threadIdx.x, dead, &a.ws->abort, limit);
+            } else {
+                c = a.ws->recv[0];
+                for (int r = 1; r < a.n_ranks; ++r) {
+                    const Cand o = a.ws->recv[r];
+                    if (cand_better(o.v, o.i, c.v, c.i)) c = o;
+                }
+            }
+            if (!dead && c.i >= (unsigned long long)a.n) dead = kAbortIndex;
+            if (dead) {
+                c.i = 0xffffffffull;
+                if (threadIdx.x == 0 && ld_volatile_u32(&a.ws->abort) == 0u) a.ws->abort = dead;
+                if (mail && dead != kAbortPeer) mail_poison(a.ws->mail, a.n_ranks, threadIdx.x);
+            }
         }
-        __syncthreads();
-        return win_bc;
+        if (threadIdx.x == 0) win_bc = c;
     }
-    Cand best = a.ws->recv[0];
-    for (int r = 1; r < a.n_ranks; ++r) {
-        const Cand c = a.ws->recv[r];
-        if (cand_better(c.v, c.i, best.v, best.i)) best = c;
-    }
-    return best;
+    __syncthreads();
+    return win_bc;
 }
+
+__device__ __forceinline__ bool winner_ok(const Cand& win) { return win.i != 0xffffffffull; }
 
 // grid-level argmin: block result -> partial[], last block reduces partial[] -> ws->send
 // (single rank: the exchange is the identity, so the result goes straight into recv[0])
@@ -379,6 +457,7 @@ __global__ void __launch_bounds__(kThreads) thin_init_kernel(ThinArgs<T> a) {
 template <typename T, int D, bool STRICT, int ITEMS>
 __global__ void __launch_bounds__(kThreads) thin_step_small_kernel(ThinArgs<T> a) {
     const Cand win = pick_winner(a);
+    if (!winner_ok(win)) return;                 // job aborted (block-uniform): nothing is read, nothing is published
     const long long sel = (long long)win.i;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
     T y[D], sy[D];
@@ -444,6 +523,7 @@ __global__ void thin_step_tiled_kernel(ThinArgs<T> a) {
     T* xlt = st + (size_t)TR * ld;
 
     const Cand win = pick_winner(a);
+    if (!winner_ok(win)) return;                 // job aborted (block-uniform): nothing is read, nothing is published
     const long long sel = (long long)win.i;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
     for (int k = threadIdx.x; k < d; k += TR) {
@@ -517,6 +597,7 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
     T* xlt = st + kThreads * kChunkLd;
 
     const Cand win = pick_winner(a);
+    if (!winner_ok(win)) return;                 // job aborted (block-uniform): nothing is read, nothing is published
     const long long sel = (long long)win.i;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
     for (int k = threadIdx.x; k < d; k += kThreads) {
@@ -763,6 +844,7 @@ __global__ void __launch_bounds__(kThreads, 1) thin_step_chunked_pipe_kernel(Thi
     T* ring = ylsh + d;                                       // NST x { xt, st, (xlt) } of kThreads x kChunkLd
 
     const Cand win = pick_winner(a);
+    if (!winner_ok(win)) return;                 // job aborted (block-uniform): nothing is read, nothing is published
     const long long sel = (long long)win.i;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
     for (int k = threadIdx.x; k < d; k += kThreads) {
@@ -1129,8 +1211,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
             if (tid < 32) {
                 double wv = __longlong_as_double(0x7ff0000000000000LL);
                 unsigned wi = 0xffffffffu;
-                bool dead = false;
+                unsigned dead = 0;                                  // kAbort* code, warp-uniform after each stage
                 unsigned long long* bc = ws->bcast[step & 1];
+                const unsigned long long limit = ws->spin_ns;
+                // the first cross-rank exchange absorbs the skew between the ranks' host threads
+                const unsigned long long limit_x = (MULTI && step == 0) ? ws->spin_first_ns : limit;
                 if (!MULTI || blockIdx.x == 0) {
                     // gather.  Single rank: warp 0 of EVERY CTA polls all per-CTA slots and reduces them itself
                     // (one store->load hop per step).  Multi rank: only CTA 0 gathers, then talks to the peers
@@ -1142,7 +1227,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
 #pragma unroll
                     for (int q = 0; q < kPollPerLane; ++q)
                         if (tid + 32u * q < gridDim.x) pending |= 1u << q;
-                    unsigned spins = 0;
+                    SpinDeadline dl;
 #pragma unroll 1
                     while (pending) {
 #pragma unroll
@@ -1161,43 +1246,52 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                                 if (cand_better(pv, pi, wv, wi)) { wv = pv; wi = pi; }
                             }
                         }
-                        if (pending && (++spins > kSpinLimit || ld_volatile_u32(&ws->abort))) { dead = true; break; }
-                        if (pending) GFK_SPIN_HINT();
+                        if (pending) {
+                            if (ld_volatile_u32(&ws->abort) || dl.expired(limit)) { dead = kAbortTimeout; break; }
+                            GFK_SPIN_HINT();
+                        }
                     }
-                    dead = __any_sync(0xffffffffu, dead);
+                    dead = __any_sync(0xffffffffu, dead != 0u) ? kAbortTimeout : 0u;
                     warp_argmin(wv, wi);
                     GFK_STAMP(step, 3);
                     if (MULTI && !dead) {
                         // cross-GPU stage: store this rank's winner into every peer's mailbox over NVLink, wait
                         // for all ranks' winners in the local mailbox, reduce
-                        const Cand g = mail_exchange(ws->mail, a.n_ranks, step, wv, wi, tid, true, dead, &ws->abort);
+                        const Cand g = mail_exchange(ws->mail, a.n_ranks, step, wv, wi, tid, true, dead, &ws->abort, limit_x);
                         wv = g.v;
-                        wi = g.i;
+                        wi = (unsigned)g.i;
                     }
-                    // broadcast: one flag-in-data slot that the other CTAs poll
-                    if (MULTI && tid == 0) slot_store(bc, tag16, wv, wi);
+                    if (!dead && (unsigned long long)wi >= (unsigned long long)a.n) dead = kAbortIndex;
+                    if (MULTI && dead && dead != kAbortPeer) mail_poison(ws->mail, a.n_ranks, tid);   // peers leave too
+                    // broadcast: one flag-in-data slot that the other CTAs poll (nothing on failure: they see ws->abort)
+                    if (MULTI && !dead && tid == 0) slot_store(bc, tag16, wv, wi);
                 } else {
                     unsigned long long w0 = 0, w1 = 0;
                     if (tid == 0) {
-                        unsigned spins = 0;
+                        SpinDeadline dl;
 #pragma unroll 1
                         for (;;) {
                             slot_load(bc, w0, w1);
                             if (slot_ready(w0, w1, tag16)) break;
-                            if (++spins > kSpinLimit || ld_volatile_u32(&ws->abort)) { dead = true; break; }
+                            if (ld_volatile_u32(&ws->abort) || dl.expired(limit + 2 * limit_x)) { dead = kAbortTimeout; break; }
                             GFK_SPIN_HINT();
                         }
                     }
-                    dead = __any_sync(0xffffffffu, dead);
+                    dead = __shfl_sync(0xffffffffu, dead, 0);
                     w0 = __shfl_sync(0xffffffffu, w0, 0);
                     w1 = __shfl_sync(0xffffffffu, w1, 0);
                     slot_decode(w0, w1, wv, wi);
+                    if (!dead && (unsigned long long)wi >= (unsigned long long)a.n) dead = kAbortIndex;
                 }
                 GFK_STAMP(step, 4);
                 if (tid == 0) {
-                    if (dead) { abort_sh = 1; ws->abort = 1; }
+                    if (dead) {
+                        abort_sh = 1;
+                        if (ld_volatile_u32(&ws->abort) == 0u) ws->abort = dead;
+                        wi = 0u;                                   // never used: every thread leaves below
+                    }
                     win_sh = wi;
-                    if (blockIdx.x == 0) {
+                    if (blockIdx.x == 0 && !dead) {
                         a.idx_out[step] = wi;
                         if (step == m - 1) { ws->send.v = wv; ws->send.i = wi; ws->recv[0] = ws->send; ws->step = (unsigned)m; }
                     }
@@ -1316,12 +1410,35 @@ __global__ void thin_finish_kernel(ThinArgs<T> a) {
     }
 }
 
-__global__ void thin_reset_kernel(ThinWs* ws, MailArgs mail) {
+// GFK_SPIN_MS / GFK_SPIN_FIRST_MS (milliseconds; defaults 200 and 5000) -> nanoseconds
+static unsigned long long env_ms_to_ns(const char* name, double def_ms) {
+    double ms = def_ms;
+    if (const char* e = getenv(name)) {
+        char* end = nullptr;
+        const double v = strtod(e, &end);
+        if (end != e && v > 0.0 && v < 3.6e6) ms = v;
+    }
+    return (unsigned long long)(ms * 1e6);
+}
+#if defined(GFK_SIMT_HOST)
+constexpr double kSpinMsDefault = 120000.0;   // emulated CTAs are OS threads sharing a few cores
+#else
+constexpr double kSpinMsDefault = 200.0;
+#endif
+static unsigned long long spin_limit_ns() { return env_ms_to_ns("GFK_SPIN_MS", kSpinMsDefault); }
+static unsigned long long spin_first_limit_ns() {
+    const unsigned long long a = env_ms_to_ns("GFK_SPIN_FIRST_MS", 5000.0), b = spin_limit_ns();
+    return a > b ? a : b;
+}
+
+__global__ void thin_reset_kernel(ThinWs* ws, MailArgs mail, unsigned long long spin_ns, unsigned long long spin_first_ns) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ws->counter = 0;
         ws->step = 0;
         ws->abort = 0;
         ws->mail = mail;
+        ws->spin_ns = spin_ns;
+        ws->spin_first_ns = spin_first_ns;
     }
     unsigned long long* ll = &ws->ll[0][0][0];
     for (int e = threadIdx.x; e < 2 * (kMaxBlocks / 2) * 4; e += blockDim.x) ll[e] = 0ull;
@@ -1411,7 +1528,7 @@ static int persistent_go2(const ThinArgs<T>& a, const MailArgs& mail, int m, int
                           unsigned grid, int threads, size_t smem, cudaStream_t st) {
     cudaError_t e = persistent_prepare(thin_persistent_kernel<T, D, STRICT, MULTI, WDD, TM>, threads, smem);
     if (e != cudaSuccess) return 0;
-    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail);
+    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail, spin_limit_ns(), spin_first_limit_ns());
     e = launch_cooperative(thin_persistent_kernel<T, D, STRICT, MULTI, WDD, TM>, grid, threads, smem, st, a, m, rpt,
                            rpt_res, rpt_tm);
     if (e != cudaSuccess) return -cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_kernel)", __FILE__, __LINE__);
@@ -1444,8 +1561,10 @@ static int try_persistent_d(const ThinArgs<T>& a, const MailArgs& mail, int m, c
     long long grid = (rows + threads - 1) / threads;
     if (grid > sms) grid = sms;
     if (grid > 32 * kPollPerLane) grid = 32 * kPollPerLane;
+    if (grid < 1) grid = 1;                              // an empty shard still takes part in every exchange
     const long long TT = grid * threads;
-    const int rpt = (int)((rows + TT - 1) / TT);
+    int rpt = (int)((rows + TT - 1) / TT);
+    if (rpt < 1) rpt = 1;
     const size_t slots = (size_t)rpt * threads;
     const size_t base = slots * (sizeof(double) + (a.lw ? sizeof(T) : 0));
     const size_t budget = (size_t)smem_optin - 1024;   // minus the kernel's static shared memory
@@ -1494,7 +1613,7 @@ static int try_persistent(const ThinArgs<T>& a, const MailArgs& mail, int d, int
 
 template <typename T, bool STRICT>
 static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, int32_t m,
-                      double* objective, uint32_t* idx_out, void* ws_raw, cudaStream_t st) {
+                      double* objective, uint32_t* idx_out, void* ws_raw, cudaStream_t st, MailArgs mail) {
     ThinArgs<T> a;
     a.x = static_cast<const T*>(p->x);
     a.s = static_cast<const T*>(p->s);
@@ -1504,17 +1623,12 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     a.A = objective;
     a.row_begin = row_begin;
     a.row_end = row_end;
+    a.n = p->n;
     a.kp = KParams{p->lambda, p->lambda_sq, p->trace, p->c, p->d, p->xl != nullptr};
     a.ws = static_cast<ThinWs*>(ws_raw);
     a.idx_out = idx_out;
     a.n_ranks = comm_size();
     a.step = 0;
-    MailArgs mail;
-    p2p_next_job(&mail, m);
-    if (a.n_ranks == 1) mail.enabled = 0;
-    if (const char* penv = getenv("GFK_P2P")) {
-        if (penv[0] == '0') mail.enabled = 0;        // force the NCCL exchange (A/B measurements)
-    }
     a.mail_enabled = mail.enabled;
     const int d = p->d;
     const long long rows = row_end - row_begin;
@@ -1569,7 +1683,7 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
                            : use_chunked ? grid_for(kThreads, chunked_smem > 72 * 1024 ? 2 : 3)
                                          : grid_for(tiled_threads, tiled_smem > 50 * 1024 ? 2 : 4);
 
-    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail);
+    thin_reset_kernel<<<1, 1024, 0, st>>>(a.ws, mail, spin_limit_ns(), spin_first_limit_ns());
     a.step = 0;                                  // produces exchange 0
     thin_init_kernel<T, STRICT><<<grid_init, kThreads, 0, st>>>(a);
     GFK_CHECK_LAUNCH();
@@ -1590,16 +1704,25 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     return GFK_OK;
 }
 
-// exchange-only loop over the peer mailboxes: measures the per-step cost of the cross-GPU stage alone
-__global__ void mail_selftest_kernel(MailArgs m, int n_ranks, int iters, unsigned* failed) {
+// exchange-only loop over the peer mailboxes: measures the per-step cost of the cross-GPU stage alone.
+// failed: 0 ok, otherwise a kAbort* code (a rank that gives up tells its peers, so all leave within one deadline)
+// or 0x100 for a record that arrived with the wrong content
+__global__ void mail_selftest_kernel(MailArgs m, int n_ranks, int iters, unsigned long long first_ns,
+                                     unsigned long long spin_ns, unsigned* failed) {
     const int lane = threadIdx.x;
-    bool any_dead = false;
+    unsigned status = 0;
     for (int it = 0; it < iters; ++it) {
-        bool dead;
-        const Cand c = mail_exchange(m, n_ranks, it, (double)(it + 1), (unsigned)(m.rank + 1), lane, true, dead, nullptr);
-        any_dead = any_dead || dead || c.v != (double)(it + 1) || c.i != 1u;
+        unsigned dead;
+        const Cand c = mail_exchange(m, n_ranks, it, (double)(it + 1), (unsigned)(m.rank + 1), lane, true, dead, nullptr,
+                                     it == 0 ? first_ns : spin_ns);
+        if (dead) {
+            if (dead != kAbortPeer) mail_poison(m, n_ranks, lane);
+            status = dead;
+            break;
+        }
+        if (c.v != (double)(it + 1) || c.i != 1u) status = 0x100u;
     }
-    if (lane == 0) *failed = any_dead ? 1u : 0u;
+    if (lane == 0) *failed = status;
 }
 
 }  // namespace gfk
@@ -1617,7 +1740,7 @@ extern "C" int gfk_p2p_selftest(int iters, double* us_per_exchange_host, void* s
     GFK_CUDA(cudaEventCreate(&e0));
     GFK_CUDA(cudaEventCreate(&e1));
     GFK_CUDA(cudaEventRecord(e0, st));
-    mail_selftest_kernel<<<1, 32, 0, st>>>(mail, comm_size(), iters, failed);
+    mail_selftest_kernel<<<1, 32, 0, st>>>(mail, comm_size(), iters, spin_first_limit_ns(), spin_limit_ns(), failed);
     GFK_CUDA(cudaEventRecord(e1, st));
     GFK_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -1628,7 +1751,12 @@ extern "C" int gfk_p2p_selftest(int iters, double* us_per_exchange_host, void* s
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     count_launches(1);
-    if (bad) { set_error("gfk_p2p_selftest: exchange failed or returned wrong data"); return GFK_ECUDA; }
+    if (bad) {
+        set_error("gfk_p2p_selftest: %s", bad == kAbortTimeout ? "a peer did not answer within the deadline (GFK_SPIN_MS)"
+                                          : bad == kAbortPeer  ? "a peer rank gave up and said so"
+                                                               : "a record arrived with the wrong content");
+        return GFK_ECUDA;
+    }
     *us_per_exchange_host = (double)ms * 1e3 / iters;
     return GFK_OK;
 }
@@ -1644,8 +1772,11 @@ extern "C" int gfk_thin_check(const void* ws, void* stream) {
                              cudaMemcpyDeviceToHost, st));
     GFK_CUDA(cudaStreamSynchronize(st));
     if (flag) {
-        set_error("gfk_thin: the persistent kernel gave up waiting for a block or a peer rank (exchange timed out); "
-                  "the index vector is invalid");
+        set_error("gfk_thin: job aborted on the device (%s); the index vector is invalid",
+                  flag == kAbortTimeout ? "a wait for another block or a peer rank ran past its deadline, GFK_SPIN_MS"
+                  : flag == kAbortPeer  ? "a peer rank aborted the job"
+                  : flag == kAbortIndex ? "an exchanged row index was out of range"
+                                        : "unknown code");
         return GFK_ECUDA;
     }
     return GFK_OK;
@@ -1654,11 +1785,22 @@ extern "C" int gfk_thin_check(const void* ws, void* stream) {
 extern "C" int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end, int32_t m,
                         double* objective, uint32_t* idx_out, void* ws, void* stream) {
     using namespace gfk;
-    GFK_REQUIRE(p && p->x && p->s && objective && idx_out && ws, "gfk_thin: NULL pointer argument");
+    // The mailbox epoch advances on EVERY call, before anything can fail on this rank alone: ranks make the same
+    // sequence of gfk_thin calls, so a rank-local argument error must not leave the tags of later jobs out of step.
+    MailArgs mail;
+    p2p_next_job(&mail, m > 0 ? m : 1);
+    {
+        // Peer mailboxes are opt-in (GFK_P2P=1): the multi-rank default is the NCCL all-gather exchange.
+        const char* penv = getenv("GFK_P2P");
+        if (comm_size() == 1 || !(penv && penv[0] == '1')) mail.enabled = 0;
+    }
+    GFK_REQUIRE(p && p->x && p->s && idx_out && ws, "gfk_thin: NULL pointer argument");
+    GFK_REQUIRE(objective || row_begin == row_end, "gfk_thin: NULL objective for a non-empty shard");
     GFK_REQUIRE(p->n >= 1 && p->n <= 0xfffffffeLL, "gfk_thin: n = %lld out of range [1, 2^32-2]", (long long)p->n);
     GFK_REQUIRE(p->d >= 1, "gfk_thin: d = %d must be >= 1", p->d);
     GFK_REQUIRE(m >= 1, "gfk_thin: m = %d must be >= 1", m);
-    GFK_REQUIRE(row_begin >= 0 && row_begin < row_end && row_end <= p->n,
+    // an empty shard (more ranks than rows) is legal: the rank offers (+inf, no index) in every exchange
+    GFK_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= p->n && (row_begin < row_end || comm_size() > 1),
                 "gfk_thin: row range [%lld, %lld) invalid for n = %lld", (long long)row_begin, (long long)row_end,
                 (long long)p->n);
     GFK_REQUIRE(!(p->xl && p->mode == GFK_F64_STRICT),
@@ -1680,9 +1822,9 @@ extern "C" int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end
                     "gfk_thin: in the strict mode w holds (hi, lo) pairs and must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (p->mode) {
-        case GFK_F64_STRICT: return thin_typed<double, true>(p, row_begin, row_end, m, objective, idx_out, ws, st);
-        case GFK_F64_FAST: return thin_typed<double, false>(p, row_begin, row_end, m, objective, idx_out, ws, st);
-        case GFK_F32_FAST: return thin_typed<float, false>(p, row_begin, row_end, m, objective, idx_out, ws, st);
+        case GFK_F64_STRICT: return thin_typed<double, true>(p, row_begin, row_end, m, objective, idx_out, ws, st, mail);
+        case GFK_F64_FAST: return thin_typed<double, false>(p, row_begin, row_end, m, objective, idx_out, ws, st, mail);
+        case GFK_F32_FAST: return thin_typed<float, false>(p, row_begin, row_end, m, objective, idx_out, ws, st, mail);
         default: set_error("gfk_thin: unknown mode %d", p->mode); return GFK_EINVAL;
     }
 }

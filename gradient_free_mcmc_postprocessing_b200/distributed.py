@@ -48,8 +48,13 @@ def nccl_library_path():
     return None
 
 
-def init(group=None, p2p=True):
-    """Collective.  Creates the libgfk communicator mirroring the torch.distributed group."""
+def init(group=None, p2p=None):
+    """Collective.  Creates the libgfk communicator mirroring the torch.distributed group.
+
+    The per-step exchange of the greedy search defaults to a 16-byte ``ncclAllGather``.  The peer-memory mailboxes
+    (CUDA IPC over NVLink, exchange fused into the thinning kernels) are opt-in: ``p2p=True`` or ``GFK_P2P=1`` in
+    the environment of EVERY rank.  A failed mailbox exchange ends in ``GfkError`` on all ranks within
+    ``GFK_SPIN_MS`` (default 200 ms; csrc/thin.cu "failure protocol"), never in a hang."""
     import torch.distributed as dist
     lib = _lib.load()
     if not dist.is_initialized():
@@ -72,8 +77,13 @@ def init(group=None, p2p=True):
             dist.broadcast(uid, src=0, group=group)
     raw = uid.numpy().tobytes()
     _lib.check(lib.gfk_comm_init(world, rank, raw, path_b))
-    if world > 1 and p2p and os.environ.get('GFK_P2P', '1') != '0':
+    if p2p is None:
+        p2p = os.environ.get('GFK_P2P', '0') == '1'
+    if world > 1 and p2p:
+        os.environ['GFK_P2P'] = '1'              # the library reads it per job
         _open_mailboxes(group, world, rank)
+    else:
+        os.environ['GFK_P2P'] = '0'
     return world, rank
 
 

@@ -108,10 +108,26 @@ def _ksd_batched(integrand, n, max_pairs=1 << 22):
     return low, diag
 
 
-def ksd_callable(integrand, n):
+def _evaluates_elementwise(integrand, n):
+    """Does the foreign callable accept two equal-length index arrays and pair them element-wise?  Decided by ONE
+    two-pair probe against the (array, [t]) form every integrand supports; the answer only selects the calling
+    pattern, so whatever the probe raises is not an error yet - a genuine defect of the callable resurfaces,
+    unswallowed, in the pattern that is then used."""
+    if n < 2:
+        return False
     try:
-        low, diag = _ksd_batched(integrand, n)
-    except Exception:   # noqa: BLE001 - whatever a foreign callable raises when given a form it does not support
+        both = np.asarray(integrand(np.array([0, 1]), np.array([1, 0])), dtype=float)
+        one = np.asarray(integrand(np.array([0]), [1]), dtype=float)
+    except Exception:   # noqa: BLE001 - a probe; see the docstring
+        return False
+    return both.shape == (2,) and one.reshape(-1).shape == (1,) and \
+        (both[0] == one.reshape(-1)[0] or (np.isnan(both[0]) and np.isnan(one.reshape(-1)[0])))
+
+
+def ksd_callable(integrand, n):
+    if _evaluates_elementwise(integrand, n):
+        low, diag = _ksd_batched(integrand, n)           # errors propagate
+    else:
         low, diag = _ksd_rows(integrand, n)              # a callable that only supports the (array, [t]) form
     ks = np.empty(n)
     total = 0.0

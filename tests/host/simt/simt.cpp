@@ -1,4 +1,5 @@
 // simt.cpp - fiber scheduler and fake CUDA runtime of the SIMT emulator (see simt.h).  TEST INFRASTRUCTURE ONLY.
+#include <time.h>
 #include "simt.h"
 
 #include <fcntl.h>
@@ -306,6 +307,12 @@ void cp_async_wait(int allow_pending_groups) {
         run_copies(f->groups.front());
         f->groups.erase(f->groups.begin());
     }
+}
+
+unsigned long long now_ns() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
 
 void poll_yield() {

@@ -60,6 +60,7 @@ void named_barrier(int id, int count, bool wait);
 const unsigned long long* warp_gather(unsigned long long bits);
 unsigned warp_alive_mask();
 void poll_yield();                      // inside spin loops on memory another thread writes
+unsigned long long now_ns();            // %globaltimer: monotonic wall clock in nanoseconds
 // cp.async with its real (deferred) semantics: the bytes move no earlier than the cp_async_wait that covers their
 // group, so reading a staged buffer before waiting - or before the barrier that publishes OTHER threads' waits -
 // finds the poison pattern instead of data

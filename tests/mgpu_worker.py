@@ -20,7 +20,9 @@ def main():
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
     dist.init_process_group('nccl')
-    gdist.init()
+    # the NCCL all-gather exchange is the default; the peer-mailbox modes run only when asked for (GFK_TEST_MAILBOX=1,
+    # tools/r02_contact_n2.sh) - they are opt-in in the product too
+    gdist.init(p2p=os.environ.get('GFK_TEST_MAILBOX') == '1')
     warnings.simplefilter('ignore')
     from gradient_free_mcmc_postprocessing_b200 import _lib
     p2p = bool(_lib.load().gfk_p2p_enabled())
@@ -36,7 +38,7 @@ def main():
     g10 = -x10 * (1 + 0.1 * np.arange(10))
     expect10 = ot.thin(x10, g10, 40, preconditioner='med')
     # exchange through peer mailboxes (persistent + multi-launch kernels) and through NCCL all-gather
-    modes = [dict(), dict(GFK_PERSISTENT='0'), dict(GFK_P2P='0')] if p2p else [dict()]
+    modes = [dict(GFK_P2P='1'), dict(GFK_P2P='1', GFK_PERSISTENT='0'), dict(GFK_P2P='0')] if p2p else [dict(GFK_P2P='0')]
     for env in modes:
         for k in ('GFK_PERSISTENT', 'GFK_P2P'):
             os.environ.pop(k, None)
@@ -52,8 +54,8 @@ def main():
         dist.barrier()
         if rank == 0:
             print('mode ok:', env, flush=True)
-    for k in ('GFK_PERSISTENT', 'GFK_P2P'):
-        os.environ.pop(k, None)
+    os.environ.pop('GFK_PERSISTENT', None)
+    os.environ['GFK_P2P'] = '0'
     got = expect1
     # every rank returns the same sequence
     t = torch.from_numpy(got.astype(np.int64)).cuda()

@@ -37,7 +37,7 @@ def main():
     torch.cuda.device = lambda dev: contextlib.nullcontext()
     gdist.nccl_library_path = lambda: os.path.join(HERE, 'host', 'libfake_nccl.so')
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    assert gdist.init() == (world, rank)
+    assert gdist.init(p2p=True) == (world, rank)        # mailboxes are opt-in; the default is covered by the last mode
     assert _lib.load().gfk_p2p_enabled() == 1
 
     rng = np.random.default_rng(77)
@@ -49,7 +49,7 @@ def main():
     g = np.ascontiguousarray(-(x - 0.1) * (1.0 + 0.2 * np.arange(d)))
     log_p = -0.5 * np.sum(x ** 2, axis=1)
     log_q = log_p + 0.5 * np.sin(x[:, 0])
-    for env in (dict(), dict(GFK_PERSISTENT='0'), dict(GFK_P2P='0')):
+    for env in (dict(GFK_P2P='1'), dict(GFK_P2P='1', GFK_PERSISTENT='0'), dict(GFK_P2P='0')):
         for k in ('GFK_PERSISTENT', 'GFK_P2P'):
             os.environ.pop(k, None)
         os.environ.update(env)

@@ -85,7 +85,8 @@ def main():
     expect2 = ot.thin(x2, g2, 30)
     x10, g10 = _mcmc_like(rng, 1200, 10)
     expect10 = ot.thin(x10, g10, 20, preconditioner='med')
-    for env in (dict(), dict(GFK_PERSISTENT='0'), dict(GFK_P2P='0')):
+    # peer mailboxes are opt-in (GFK_P2P=1); the default multi-rank exchange is the NCCL all-gather
+    for env in (dict(GFK_P2P='1'), dict(GFK_P2P='1', GFK_PERSISTENT='0'), dict()):
         for k in ('GFK_PERSISTENT', 'GFK_P2P'):
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -99,6 +100,12 @@ def main():
             p = H.SimProblem(x10, g10, preconditioner='med', precision=precision)
             idx, _ = p.thin(20, row_range=shard_bounds(p.n, world, rank))
             assert np.array_equal(idx, expect10), (rank, env, precision)
+        # more ranks than rows: a rank without rows offers (+inf, no index) in every exchange
+        for nt in (1, 2):
+            xt, gt = np.ascontiguousarray(x2[5:5 + nt]), np.ascontiguousarray(g2[5:5 + nt])
+            p = H.SimProblem(xt, gt, standardize=False)
+            idx, _ = p.thin(6, row_range=shard_bounds(nt, world, rank))
+            assert np.array_equal(idx, ot.thin(xt, gt, 6, standardize=False)), (rank, env, nt, idx)
     for k in ('GFK_PERSISTENT', 'GFK_P2P'):
         os.environ.pop(k, None)
 

@@ -6,7 +6,7 @@ from gradient_free_mcmc_postprocessing_b200 import _lib, distributed as gdist
 
 torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
 dist.init_process_group('nccl')
-gdist.init()
+gdist.init(p2p=True)
 lib = _lib.load()
 for iters in (1000, 20000, 20000):
     us = ctypes.c_double()
