@@ -203,7 +203,13 @@ class SteinProblem:
                 m2 = m2 / np.log(np.minimum(MEDIAN_SUBSAMPLE, n))
             linv = scalar_linv(m2, d)
         elif preconditioner == 'smpcov':
-            cov = np.atleast_2d(torch.cov(self.x.T).cpu().numpy())
+            if n < 2:
+                raise Exception('Too few unique samples in sample.')
+            lib = _lib.load()
+            ws = _bytes(lib.gfk_covariance_ws_bytes(n, d), self.device)
+            cov_host = (ctypes.c_double * (d * d))()
+            check(lib.gfk_covariance(_ptr(self.x), n, d, cov_host, _ptr(ws), _stream_ptr(self.device)))
+            cov = np.array(cov_host[:]).reshape(d, d)
             if not np.all(np.linalg.eigvals(cov) > 0):
                 raise Exception('Too few unique samples in sample.')
             linv = dense = np.linalg.inv(cov)
@@ -226,7 +232,10 @@ class SteinProblem:
                                  "x' L L x with L as given, which the device formulation reproduces only for "
                                  'symmetric L' % asym)
             sym = 0.5 * (dense + dense.T)          # removes rounding-level asymmetry only
-            self.xl = self.x @ torch.from_numpy(sym).to(self.device)
+            lib = _lib.load()
+            sym_dev = torch.from_numpy(np.ascontiguousarray(sym)).to(self.device)
+            self.xl = torch.empty_like(self.x)
+            check(lib.gfk_rows_times_matrix(_ptr(self.x), n, d, _ptr(sym_dev), _ptr(self.xl), _stream_ptr(self.device)))
             self.lam = self.lam_sq = 1.0
             if self.mode == _lib.F64_STRICT:
                 # numpy's BLAS summation order for np.dot(linv, .) is not reproducible: no strict formulation exists

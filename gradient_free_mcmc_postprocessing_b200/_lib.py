@@ -48,6 +48,9 @@ PROTOTYPES = {
     'gfk_standardize': (ctypes.c_int, [_vp, _vp, _i64, _i32, ctypes.c_int, _vp, _vp, _pd, _vp, _vp]),
     'gfk_median_ws_bytes': (_sz, [_i64, _i32]),
     'gfk_median_pdist': (ctypes.c_int, [_vp, _i64, _i32, _i32, _pd, _vp, _vp]),
+    'gfk_covariance_ws_bytes': (_sz, [_i64, _i32]),
+    'gfk_covariance': (ctypes.c_int, [_vp, _i64, _i32, _pd, _vp, _vp]),
+    'gfk_rows_times_matrix': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     'gfk_to_f32': (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     'gfk_log_weights_ws_bytes': (_sz, []),
     'gfk_log_weights': (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, _dbl, _vp, _pd, _vp, _vp]),

@@ -6,10 +6,13 @@
 //
 // gfk_ksd_rowsums: one CTA per 64-row tile I walks the column tiles J <= I.  Row and column tiles
 // are staged in shared memory transposed ([k][row], conflict-free), in chunks of KC dimensions so any
-// d fits; each thread owns 4 rows x 4 columns (columns strided by 16, so a half-warp reads one conflict-free
-// 128-byte line per shared-memory load) and keeps the three running dot products
+// d fits; each thread owns MTR rows x MTC columns (columns strided by TILE / MTC, so a warp reads conflict-free
+// 128-byte lines per shared-memory load) and keeps the three running dot products
 // (<r,r>, <ds,r>, <sx,sy>) of every pair in registers - a GEMM-shaped loop on the FP64 (or FP32)
-// FMA pipe with ~0 bytes of HBM traffic per pair.  Row sums are reduced in a fixed order (no
+// FMA pipe with ~0 bytes of HBM traffic per pair.  float64: 4 x 2 pairs per thread, 512 threads per CTA (round 1's
+// 4 x 4 / 256-thread shape needed 176 registers, i.e. 8 warps per SM that stalled together at the two barriers of
+// every stage: FP64 pipe ~39 % busy; 4 x 2 fits 128 registers, so the SM holds 16 warps - same tile, same shared
+// memory, same operation order per pair).  float32 keeps 4 x 4 / 256 threads (two CTAs per SM).  Row sums are reduced in a fixed order (no
 // atomics), so results are run-to-run reproducible and independent of the GPU count.
 #include <stdlib.h>
 
@@ -19,8 +22,10 @@ namespace gfk {
 
 constexpr int TILE = 64;     // rows / columns per tile
 constexpr int LD = TILE + 2; // padded leading dimension of a staged tile: keeps 16-byte alignment per k
-constexpr int MT = 4;        // micro-tile edge (pairs per thread = MT * MT)
-constexpr int KSD_THREADS = (TILE / MT) * (TILE / MT);  // 256
+constexpr int MTR = 4;       // rows of the tile per thread
+// columns of the tile per thread and the resulting CTA size
+template <typename T> struct KsdShape { static constexpr int MTC = 4; static constexpr int THREADS = (TILE / MTR) * (TILE / 4); };
+template <> struct KsdShape<double> { static constexpr int MTC = 2; static constexpr int THREADS = (TILE / MTR) * (TILE / 2); };
 
 template <typename T>
 struct KsdArgs {
@@ -78,9 +83,10 @@ template <typename T, int KC>
 __device__ __forceinline__ void stage_tile(const KsdArgs<T>& a, const T* __restrict__ src, long long t0, int k0,
                                            int kc, T* __restrict__ dst) {
     const int d = a.kp.d;
+    constexpr int NT = KsdShape<T>::THREADS;
     int r = (int)threadIdx.x / kc, k = (int)threadIdx.x - r * kc;
-    const int dr = KSD_THREADS / kc, dk = KSD_THREADS - dr * kc;
-    for (int e = threadIdx.x; e < TILE * kc; e += KSD_THREADS) {
+    const int dr = NT / kc, dk = NT - dr * kc;
+    for (int e = threadIdx.x; e < TILE * kc; e += NT) {
         const long long t = t0 + r;
         if (t < a.m) cp_async_elem(dst + k * LD + r, src + row_of(a, t) * d + k0 + k);
         else dst[k * LD + r] = T(0);
@@ -94,9 +100,11 @@ __device__ __forceinline__ void stage_tile(const KsdArgs<T>& a, const T* __restr
 // Stages are the (column tile J, dimension chunk k0) pairs in order; stage s+1 is copied in with cp.async
 // while stage s is consumed.  With d <= KC the row tile is invariant and staged once into buffer 0's row slots.
 template <typename T, bool DENSE, int KC>
-__global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
+__global__ void __launch_bounds__(KsdShape<T>::THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
     extern __shared__ __align__(16) unsigned char ksd_smem[];
     constexpr int NARR = DENSE ? 6 : 4;
+    constexpr int MTC = KsdShape<T>::MTC;
+    constexpr int CG = TILE / MTC;            // column groups = threads that share a row (consecutive lanes)
     T* buf0 = reinterpret_cast<T*>(ksd_smem);
     T* buf1 = buf0 + NARR * KC * LD;
     T* wr = buf1 + NARR * KC * LD;
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
     if ((long long)blockIdx.x >= my_tiles) return;
     const long long I = a.part + (my_tiles - 1 - blockIdx.x) * (long long)a.n_parts;
     const long long t0 = I * TILE;
-    const int ty = threadIdx.x / (TILE / MT), tx = threadIdx.x % (TILE / MT);
+    const int ty = threadIdx.x / CG, tx = threadIdx.x % CG;
     const int d = a.kp.d;
     const bool gf = (a.lw != nullptr);
     const bool pre_w = (a.w != nullptr);
@@ -152,10 +160,10 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
     }
     issue(0);
 
-    double rowacc[MT];
+    double rowacc[MTR];
 #pragma unroll
-    for (int i = 0; i < MT; ++i) rowacc[i] = 0.0;
-    T rr[MT][MT], su[MT][MT], ss[MT][MT], uu[DENSE ? MT : 1][DENSE ? MT : 1];
+    for (int i = 0; i < MTR; ++i) rowacc[i] = 0.0;
+    T rr[MTR][MTC], su[MTR][MTC], ss[MTR][MTC], uu[DENSE ? MTR : 1][DENSE ? MTC : 1];
 
     for (long long stage = 0; stage < nstages; ++stage) {
         const long long J = stage / nchunks;
@@ -178,31 +186,32 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
         const T* xlc = base + 5 * KC * LD;
         if (chunk == 0) {
 #pragma unroll
-            for (int i = 0; i < MT; ++i)
+            for (int i = 0; i < MTR; ++i)
 #pragma unroll
-                for (int j = 0; j < MT; ++j) {
+                for (int j = 0; j < MTC; ++j) {
                     rr[i][j] = T(0); su[i][j] = T(0); ss[i][j] = T(0);
                     if (DENSE) uu[i][j] = T(0);
                 }
         }
 #pragma unroll 2
         for (int k = 0; k < kc; ++k) {
-            T xi[MT], si[MT], xj[MT], sj[MT], li[DENSE ? MT : 1], lj[DENSE ? MT : 1];
+            T xi[MTR], si[MTR], xj[MTC], sj[MTC], li[DENSE ? MTR : 1], lj[DENSE ? MTC : 1];
 #pragma unroll
-            for (int i = 0; i < MT; ++i) {
-                xi[i] = xr[k * LD + ty * MT + i];
-                si[i] = sr[k * LD + ty * MT + i];
-                xj[i] = xc[k * LD + tx + (TILE / MT) * i];
-                sj[i] = sc[k * LD + tx + (TILE / MT) * i];
-                if (DENSE) {
-                    li[i] = xlr[k * LD + ty * MT + i];
-                    lj[i] = xlc[k * LD + tx + (TILE / MT) * i];
-                }
+            for (int i = 0; i < MTR; ++i) {
+                xi[i] = xr[k * LD + ty * MTR + i];
+                si[i] = sr[k * LD + ty * MTR + i];
+                if (DENSE) li[i] = xlr[k * LD + ty * MTR + i];
             }
 #pragma unroll
-            for (int i = 0; i < MT; ++i)
+            for (int j = 0; j < MTC; ++j) {
+                xj[j] = xc[k * LD + tx + CG * j];
+                sj[j] = sc[k * LD + tx + CG * j];
+                if (DENSE) lj[j] = xlc[k * LD + tx + CG * j];
+            }
 #pragma unroll
-                for (int j = 0; j < MT; ++j) {
+            for (int i = 0; i < MTR; ++i)
+#pragma unroll
+                for (int j = 0; j < MTC; ++j) {
                     const T r = xi[i] - xj[j];
                     const T ds = si[i] - sj[j];
                     if (DENSE) {
@@ -221,15 +230,15 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
             // epilogue of column tile J: powers, weights, triangular mask
             const T* wc = wcb + (J & 1) * TILE;
 #pragma unroll
-            for (int i = 0; i < MT; ++i) {
-                const long long t = t0 + ty * MT + i;
+            for (int i = 0; i < MTR; ++i) {
+                const long long t = t0 + ty * MTR + i;
                 double part_sum = 0.0;
 #pragma unroll
-                for (int j = 0; j < MT; ++j) {
-                    const long long b = c0 + tx + (TILE / MT) * j;
+                for (int j = 0; j < MTC; ++j) {
+                    const long long b = c0 + tx + CG * j;
                     T kv = fast_finish<T, DENSE>(rr[i][j], DENSE ? uu[i][j] : T(0), su[i][j], ss[i][j], a.kp);
                     if (gf) {
-                        const T wi = wr[ty * MT + i], wj = wc[tx + (TILE / MT) * j];
+                        const T wi = wr[ty * MTR + i], wj = wc[tx + CG * j];
                         kv *= pre_w ? (wi * wj) : (T)exp((double)wi + (double)wj);
                     }
                     if (b < t && t < a.m) part_sum += (double)kv;
@@ -239,182 +248,13 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_rowsum_kernel(KsdArgs<T> a) {
         }
         __syncthreads();   // buffer (stage & 1) is free for the copy issued at the top of the next iteration
     }
-    // reduce the TILE/MT threads that share a row (consecutive lanes: tx = lane % 16)
+    // reduce the CG threads that share a row (consecutive lanes: tx = lane % CG; CG = 16 or 32)
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
+    for (int i = 0; i < MTR; ++i) {
         double v = rowacc[i];
 #pragma unroll
-        for (int off = (TILE / MT) / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        const long long t = t0 + ty * MT + i;
-        if (tx == 0 && t < a.m) a.low[t] = v;
-    }
-}
-
-// ---- warp-specialised variant (scalar preconditioner, d <= KC): one producer warp + eight consumer warps ----------
-// The tile kernel above couples all warps twice per stage (__syncthreads) and makes every warp execute the staging
-// address arithmetic.  Here warp 8 alone streams the column tiles through a ring of NBUF buffers with cp.async and
-// the eight consumer warps only compute; they meet through named barriers (PTX bar.sync / bar.arrive):
-//   full[b]  : producer arrives when tile J has landed in buffer b, consumers wait for it
-//   empty[b] : consumers arrive when they have finished reading buffer b, the producer waits before refilling it
-// so a consumer warp never waits for another consumer warp's epilogue.  The row tile is staged once by everybody.
-// [round 1: opt-in with GFK_KSD_WS=1; executed on the CPU emulator of the test suite only, not yet on a GPU]
-constexpr int KSD_WS_CONSUMERS = KSD_THREADS;           // 256
-constexpr int KSD_WS_THREADS = KSD_THREADS + 32;        // + the producer warp
-constexpr int KSD_WS_NBUF = 3;
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-#if defined(GFK_SIMT_HOST)
-    simt::named_barrier(id, count, true);
-#else
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-#if defined(GFK_SIMT_HOST)
-    simt::named_barrier(id, count, false);
-#else
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-}
-
-// rows [t0, t0 + TILE) x dimensions [0, d) -> dst[k][LD], by `nthr` threads starting at `tid` (zero rows beyond m)
-template <typename T>
-__device__ __forceinline__ void stage_tile_by(const KsdArgs<T>& a, const T* __restrict__ src, long long t0, int d,
-                                              T* __restrict__ dst, int tid, int nthr) {
-    int r = tid / d, k = tid - r * d;                            // one division; then (r, k) advance by nthr elements
-    const int dr = nthr / d, dk = nthr - dr * d;
-    for (int e = tid; e < TILE * d; e += nthr) {
-        const long long t = t0 + r;
-        if (t < a.m) cp_async_elem(dst + k * LD + r, src + row_of(a, t) * d + k);
-        else dst[k * LD + r] = T(0);
-        r += dr;
-        k += dk;
-        if (k >= d) { k -= d; ++r; }
-    }
-}
-
-template <typename T, int KC>
-__global__ void __launch_bounds__(KSD_WS_THREADS) ksd_rowsum_ws_kernel(KsdArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char ksd_ws_smem[];
-    T* rowbuf = reinterpret_cast<T*>(ksd_ws_smem);                 // xr, sr : 2 x KC x LD
-    T* colbuf = rowbuf + 2 * KC * LD;                              // NBUF x { xc, sc : 2 x KC x LD }
-    T* wr = colbuf + KSD_WS_NBUF * 2 * KC * LD;                    // TILE
-    T* wcb = wr + TILE;                                            // NBUF x TILE
-
-    const long long ntiles = (a.m + TILE - 1) / TILE;
-    const long long my_tiles = (ntiles - a.part + a.n_parts - 1) / a.n_parts;
-    if ((long long)blockIdx.x >= my_tiles) return;
-    const long long I = a.part + (my_tiles - 1 - blockIdx.x) * (long long)a.n_parts;
-    const long long t0 = I * TILE;
-    const int tid = threadIdx.x;
-    const int d = a.kp.d;
-    const bool gf = (a.lw != nullptr);
-    const bool pre_w = (a.w != nullptr);
-
-    // the row tile, once, by all nine warps
-    stage_tile_by<T>(a, a.x, t0, d, rowbuf, tid, KSD_WS_THREADS);
-    stage_tile_by<T>(a, a.s, t0, d, rowbuf + KC * LD, tid, KSD_WS_THREADS);
-    if (tid < TILE) {
-        const long long t = t0 + tid;
-        T v = T(0);
-        if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t) * a.wstride) : __ldg(a.lw + row_of(a, t));
-        wr[tid] = v;
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-
-    if (tid >= KSD_WS_CONSUMERS) {
-        // ---- producer warp ---------------------------------------------------------------------------------
-        const int lane = tid - KSD_WS_CONSUMERS;
-        for (long long J = 0; J <= I; ++J) {
-            const int b = (int)(J % KSD_WS_NBUF);
-            if (J >= KSD_WS_NBUF) named_bar_sync(1 + KSD_WS_NBUF + b, KSD_WS_THREADS);    // buffer b is free again
-            T* base = colbuf + (size_t)b * 2 * KC * LD;
-            const long long c0 = J * TILE;
-            stage_tile_by<T>(a, a.x, c0, d, base, lane, 32);
-            stage_tile_by<T>(a, a.s, c0, d, base + KC * LD, lane, 32);
-            for (int r = lane; r < TILE; r += 32) {
-                const long long t = c0 + r;
-                T v = T(0);
-                if (gf && t < a.m) v = pre_w ? __ldg(a.w + row_of(a, t) * a.wstride) : __ldg(a.lw + row_of(a, t));
-                wcb[b * TILE + r] = v;
-            }
-            cp_async_commit();
-            if (J >= 1) {                                         // tile J - 1 has landed: keep two tiles in flight
-                cp_async_wait<1>();
-                named_bar_arrive(1 + (int)((J - 1) % KSD_WS_NBUF), KSD_WS_THREADS);
-            }
-        }
-        cp_async_wait<0>();
-        named_bar_arrive(1 + (int)(I % KSD_WS_NBUF), KSD_WS_THREADS);
-        return;
-    }
-
-    // ---- consumer warps --------------------------------------------------------------------------------------
-    const int ty = tid / (TILE / MT), tx = tid % (TILE / MT);
-    const T* xr = rowbuf;
-    const T* sr = rowbuf + KC * LD;
-    double rowacc[MT];
-#pragma unroll
-    for (int i = 0; i < MT; ++i) rowacc[i] = 0.0;
-    for (long long J = 0; J <= I; ++J) {
-        const int b = (int)(J % KSD_WS_NBUF);
-        const long long c0 = J * TILE;
-        named_bar_sync(1 + b, KSD_WS_THREADS);                    // tile J is in buffer b
-        const T* xc = colbuf + (size_t)b * 2 * KC * LD;
-        const T* sc = xc + KC * LD;
-        const T* wc = wcb + b * TILE;
-        T rr[MT][MT], su[MT][MT], ss[MT][MT];
-#pragma unroll
-        for (int i = 0; i < MT; ++i)
-#pragma unroll
-            for (int j = 0; j < MT; ++j) { rr[i][j] = T(0); su[i][j] = T(0); ss[i][j] = T(0); }
-#pragma unroll 2
-        for (int k = 0; k < d; ++k) {
-            T xi[MT], si[MT], xj[MT], sj[MT];
-#pragma unroll
-            for (int i = 0; i < MT; ++i) {
-                xi[i] = xr[k * LD + ty * MT + i];
-                si[i] = sr[k * LD + ty * MT + i];
-                xj[i] = xc[k * LD + tx + (TILE / MT) * i];
-                sj[i] = sc[k * LD + tx + (TILE / MT) * i];
-            }
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int j = 0; j < MT; ++j) {
-                    const T r = xi[i] - xj[j];
-                    const T ds = si[i] - sj[j];
-                    rr[i][j] = fma_t(r, r, rr[i][j]);
-                    su[i][j] = fma_t(ds, r, su[i][j]);
-                    ss[i][j] = fma_t(si[i], sj[j], ss[i][j]);
-                }
-        }
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            const long long t = t0 + ty * MT + i;
-            double part_sum = 0.0;
-#pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                const long long bcol = c0 + tx + (TILE / MT) * j;
-                T kv = fast_finish<T, false>(rr[i][j], T(0), su[i][j], ss[i][j], a.kp);
-                if (gf) {
-                    const T wi = wr[ty * MT + i], wj = wc[tx + (TILE / MT) * j];
-                    kv *= pre_w ? (wi * wj) : (T)exp((double)wi + (double)wj);
-                }
-                if (bcol < t && t < a.m) part_sum += (double)kv;
-            }
-            rowacc[i] += part_sum;
-        }
-        if (J + KSD_WS_NBUF <= I) named_bar_arrive(1 + KSD_WS_NBUF + b, KSD_WS_THREADS);  // buffer b may be refilled
-    }
-#pragma unroll
-    for (int i = 0; i < MT; ++i) {
-        double v = rowacc[i];
-#pragma unroll
-        for (int off = (TILE / MT) / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        const long long t = t0 + ty * MT + i;
+        for (int off = CG / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        const long long t = t0 + ty * MTR + i;
         if (tx == 0 && t < a.m) a.low[t] = v;
     }
 }
@@ -549,11 +389,6 @@ static int grid1d(long long work) {
     return (int)(b < 1 ? 1 : b);
 }
 
-static bool ksd_ws_enabled() {
-    const char* env = getenv("GFK_KSD_WS");
-    return env && env[0] == '1';
-}
-
 template <typename T>
 static int rowsums_typed(const gfk_problem* p, const uint32_t* sel, int64_t m, int part, int n_parts, double* low,
                          double* diag, cudaStream_t st) {
@@ -571,19 +406,13 @@ static int rowsums_typed(const gfk_problem* p, const uint32_t* sel, int64_t m, i
             const size_t smem = sizeof(T) * (size_t)(2 * 6 * KC * LD + 3 * TILE);
             GFK_CUDA(cudaFuncSetAttribute(ksd_rowsum_kernel<T, true, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-            ksd_rowsum_kernel<T, true, KC><<<(unsigned)my_tiles, KSD_THREADS, smem, st>>>(a);
-        } else if (ksd_ws_enabled() && p->d <= 32) {
-            constexpr int KC = 32;
-            const size_t smem = sizeof(T) * (size_t)((1 + KSD_WS_NBUF) * 2 * KC * LD + (1 + KSD_WS_NBUF) * TILE);
-            GFK_CUDA(cudaFuncSetAttribute(ksd_rowsum_ws_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-            ksd_rowsum_ws_kernel<T, KC><<<(unsigned)my_tiles, KSD_WS_THREADS, smem, st>>>(a);
+            ksd_rowsum_kernel<T, true, KC><<<(unsigned)my_tiles, KsdShape<T>::THREADS, smem, st>>>(a);
         } else {
             constexpr int KC = 32;
             const size_t smem = sizeof(T) * (size_t)(2 * 4 * KC * LD + 3 * TILE);
             GFK_CUDA(cudaFuncSetAttribute(ksd_rowsum_kernel<T, false, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-            ksd_rowsum_kernel<T, false, KC><<<(unsigned)my_tiles, KSD_THREADS, smem, st>>>(a);
+            ksd_rowsum_kernel<T, false, KC><<<(unsigned)my_tiles, KsdShape<T>::THREADS, smem, st>>>(a);
         }
     }
     count_launches(my_tiles > 0 ? 2 : 1);

@@ -289,6 +289,46 @@ __global__ void __launch_bounds__(256) gaussian_proxy_kernel(const double* __res
     }
 }
 
+// ---- 'smpcov' preconditioner (stein_thinning.kernel.make_precon; parity unpinned) ----
+// np.cov(sample, rowvar=False): c = x - mean;  cov = c' c / (n - 1).  One block per 2048-row chunk and entry (a, b),
+// a <= b, of the chunk's partial; the chunk partials are added by col_finish_kernel in its fixed order.
+__global__ void __launch_bounds__(kRedThreads) cov_chunk_kernel(const double* __restrict__ x, long long n, int d,
+                                                                const double* __restrict__ loc,
+                                                                double* __restrict__ partial /* [nchunks][d * d] */) {
+    __shared__ double sh[kRedThreads / 32];
+    const long long r0 = (long long)blockIdx.x * kChunkRows;
+    const long long r1 = min(n, r0 + kChunkRows);
+    for (int a = 0; a < d; ++a) {
+        const double la = loc[a];
+        for (int b = a; b < d; ++b) {
+            const double lb = loc[b];
+            double acc = 0.0;
+            for (long long r = r0 + threadIdx.x; r < r1; r += kRedThreads) acc = fma(x[r * d + a] - la, x[r * d + b] - lb, acc);
+            const double tot = block_sum_256(acc, sh);
+            if (threadIdx.x == 0) {
+                partial[(long long)blockIdx.x * d * d + a * d + b] = tot;
+                partial[(long long)blockIdx.x * d * d + b * d + a] = tot;
+            }
+        }
+    }
+}
+
+// out = x @ L for a dense d x d preconditioner L (row-major, device): thread per row, L in shared memory
+__global__ void __launch_bounds__(256) rows_times_matrix_kernel(const double* __restrict__ x, long long n, int d,
+                                                                const double* __restrict__ L, double* __restrict__ out) {
+    extern __shared__ double rm_sm[];
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) rm_sm[e] = L[e];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double* xi = x + i * d;
+        for (int k = 0; k < d; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < d; ++j) acc = fma(xi[j], rm_sm[j * d + k], acc);
+            out[i * d + k] = acc;
+        }
+    }
+}
+
 static int grid_for(long long work, int threads) {
     long long b = (work + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 8;
@@ -345,6 +385,46 @@ extern "C" int gfk_standardize(const double* x, const double* g, int64_t n, int3
             }
         }
     }
+    return GFK_OK;
+}
+
+extern "C" size_t gfk_covariance_ws_bytes(int64_t n, int32_t d) {
+    const int64_t nchunks = (n + kChunkRows - 1) / kChunkRows;
+    return 64 + sizeof(double) * (size_t)((int64_t)d + (int64_t)d * d + nchunks * d * d);
+}
+
+extern "C" int gfk_covariance(const double* x, int64_t n, int32_t d, double* cov_host, void* ws, void* stream) {
+    GFK_REQUIRE(x && cov_host && ws, "gfk_covariance: NULL pointer argument");
+    GFK_REQUIRE(n >= 2 && d >= 1, "gfk_covariance: need n >= 2 and d >= 1");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* loc = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 64);
+    double* cov = loc + d;
+    double* partial = cov + (size_t)d * d;
+    const int nchunks = (int)((n + kChunkRows - 1) / kChunkRows);
+    unsigned long long* nonfinite = reinterpret_cast<unsigned long long*>(ws);
+    GFK_CUDA(cudaMemsetAsync(nonfinite, 0, 64, st));
+    col_chunk_sum_kernel<<<nchunks, kRedThreads, 0, st>>>(x, n, d, 0, nullptr, partial, nonfinite);
+    col_finish_kernel<<<1, 128, 0, st>>>(partial, nchunks, d, n, loc);
+    cov_chunk_kernel<<<nchunks, kRedThreads, 0, st>>>(x, n, d, loc, partial);
+    // the same fixed-order finish over d * d "columns", dividing by n - 1 (np.cov's default ddof = 1)
+    col_finish_kernel<<<1, 128, 0, st>>>(partial, nchunks, d * d, n - 1, cov);
+    count_launches(4);
+    GFK_CHECK_LAUNCH();
+    GFK_CUDA(cudaMemcpyAsync(cov_host, cov, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToHost, st));
+    GFK_CUDA(cudaStreamSynchronize(st));
+    return GFK_OK;
+}
+
+extern "C" int gfk_rows_times_matrix(const double* x, int64_t n, int32_t d, const double* L, double* out, void* stream) {
+    GFK_REQUIRE(x && L && out, "gfk_rows_times_matrix: NULL pointer argument");
+    GFK_REQUIRE(n >= 1 && d >= 1 && d <= 160, "gfk_rows_times_matrix: need n >= 1 and 1 <= d <= 160");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = sizeof(double) * (size_t)d * d;
+    if (smem > 48 * 1024)
+        GFK_CUDA(cudaFuncSetAttribute(rows_times_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rows_times_matrix_kernel<<<grid_for(n, 256), 256, smem, st>>>(x, n, d, L, out);
+    count_launches(1);
+    GFK_CHECK_LAUNCH();
     return GFK_OK;
 }
 

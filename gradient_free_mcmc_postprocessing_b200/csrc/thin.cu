@@ -13,8 +13,13 @@
 // produces the rank's candidate for the next exchange.  No host round trip inside the loop.
 #include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
+
+#if !defined(GFK_SIMT_HOST)
+#include <cuda.h>      // CUtensorMap and its enums only: cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint
+#endif
 
 #include "common.cuh"
 #include "comm.h"
@@ -727,32 +732,82 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
     grid_argmin_publish(bv, bi, a);
 }
 
-// ---- the same step with a software pipeline: NST slabs in flight per CTA (cp.async), one CTA per SM ----------
-// thin_step_chunked_kernel loads a slab, waits for it, consumes it, and relies on the three CTAs of an SM to overlap
-// one another.  Here ONE CTA per SM keeps NST - 1 slabs (64 KB each in float64) in flight with cp.async while it
-// consumes the oldest, so the HBM request stream never drains.  Per-row arithmetic and summation order are those of
-// thin_step_chunked_kernel (bit-identical results); the row state lives in ChunkRow so the slab loop can be
-// flattened over (tile, slab) stages.
-// [round 1: opt-in with GFK_CHUNK_PIPE=1; executed on the CPU emulator of the test suite only, not yet on a GPU]
+// ---- the same step fed by the Tensor Memory Accelerator: one CTA per SM, slabs arrive by cp.async.bulk.tensor -------
+// thin_step_chunked_kernel loads a slab with LDG, waits, consumes it, and relies on the three CTAs of an SM to overlap
+// one another (C5, d = 64: 56 % of the HBM roofline).  Here warp 8 of a 288-thread CTA is a producer: its elected
+// lane keeps kTmaStages slabs in flight with TWO instructions per slab - one 2-D bulk tensor copy each for x and s
+// ([16 dims] x [256 rows] of float64 = 32 KB per array) - and the eight consumer warps only compute.  Producer and
+// consumers meet through mbarriers: full[stage] (expect_tx bytes of both copies), empty[stage] (one arrival per
+// consumer warp); nobody executes a __syncthreads inside the loop.  The tensor maps use CU_TENSOR_MAP_SWIZZLE_128B:
+// a row of the tile is 128 bytes and its 16-byte chunks are XOR-ed with (row mod 8), so thread-per-row reads of one
+// dimension take 4 shared-memory wavefronts per warp (2 is the floor for 32 x 8 bytes; the unswizzled layout needs
+// 32).  Per-row arithmetic and summation order are those of thin_step_chunked_kernel (bit-identical results): the
+// row state lives in ChunkRow, the slab loop is flattened over (tile, slab) stages.  Rows past the end of the sample
+// and dimensions past d are zero-filled by the copy engine and never read.
+// [round 2: opt-in with GFK_STEP_TMA=1; executed on the CPU emulator of the test suite only, not yet on a GPU]
 #if defined(GFK_SIMT_HOST)
-__device__ __forceinline__ void cp_async8(double* dst, const double* src) { simt::cp_async(dst, src, 8); }
-__device__ __forceinline__ void cp_async8(float* dst, const float* src) { simt::cp_async(dst, src, 4); }
-__device__ __forceinline__ void cp_async_commit_group() { simt::cp_async_commit(); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { simt::cp_async_wait(N); }
+using TensorMap = simt::TensorMap2D;
+__device__ __forceinline__ void dev_mbar_init(unsigned long long* bar, int count) { simt::mbar_init(bar, count); }
+__device__ __forceinline__ void dev_mbar_fence_init() { }
+__device__ __forceinline__ void dev_mbar_arrive(unsigned long long* bar) { simt::mbar_arrive(bar); }
+__device__ __forceinline__ void dev_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) { simt::mbar_arrive_expect_tx(bar, bytes); }
+__device__ __forceinline__ void dev_mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (!simt::mbar_test(bar, parity)) simt::poll_yield();
+}
+__device__ __forceinline__ void dev_tma_load_2d(void* dst, const TensorMap* map, int c0, int c1, unsigned long long* bar) {
+    simt::tma_load_2d(dst, map, c0, c1, bar);
+}
 #else
-__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
+using TensorMap = CUtensorMap;
+__device__ __forceinline__ void dev_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async8(float* dst, const float* src) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src));
+// makes the initialised barriers visible to the async proxy (the copy engine) before the first copy names them
+__device__ __forceinline__ void dev_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void dev_mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}"
+                 ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void dev_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+                 ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dev_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "GFK_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GFK_MBAR_DONE;\n\t"
+        "bra GFK_MBAR_WAIT;\n\t"
+        "GFK_MBAR_DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void dev_tma_load_2d(void* dst, const TensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(reinterpret_cast<unsigned long long>(map)),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1) : "memory");
+}
 #endif
+
+constexpr int kTmaRows = 256;                        // rows of a tile = consumer threads
+constexpr int kTmaStages = 3;
+constexpr int kTmaThreads = kTmaRows + 32;           // + the producer warp
+constexpr int kTmaRowBytes = 128;                    // bytes of one tile row = the swizzle span
+template <typename T> struct TmaSlab { static constexpr int K = kTmaRowBytes / (int)sizeof(T); };   // dims per slab
+constexpr int kTmaTileBytes = kTmaRows * kTmaRowBytes;                                                // one array
+
+// row r of a SWIZZLE_128B tile: element k lives in 16-byte chunk (k * sizeof(T) / 16) XOR (r mod 8)
+template <typename T>
+struct SwizzledRow {
+    const unsigned char* row;
+    unsigned r7;
+    __device__ __forceinline__ T operator[](int k) const {
+        const unsigned byte = (unsigned)k * (unsigned)sizeof(T);
+        return *reinterpret_cast<const T*>(row + ((((byte >> 4) ^ r7) << 4) | (byte & 15u)));
+    }
+};
 
 // running sums of one row across the slabs, numpy's order (see thin_step_chunked_kernel)
 template <typename T, bool STRICT, bool DENSE>
@@ -766,7 +821,9 @@ struct ChunkRow {
         rr = uu = su = ss = T(0);
     }
 
-    __device__ __forceinline__ void slab(const T* xr, const T* sr, const T* xlr, const T* ysh, const T* sysh,
+    // xr / sr / xlr: anything indexable by k in [0, kc) - plain pointers or the swizzled rows of a TMA tile
+    template <typename AX, typename AS, typename AL>
+    __device__ __forceinline__ void slab(const AX& xr, const AS& sr, const AL& xlr, const T* ysh, const T* sysh,
                                          const T* ylsh, int k0, int kc, int d, int d8, const KParams& kp) {
         if constexpr (STRICT) {
             for (int k = 0; k < kc; ++k) {
@@ -833,106 +890,103 @@ struct ChunkRow {
     }
 };
 
-template <typename T, bool STRICT, bool DENSE, int NST>
-__global__ void __launch_bounds__(kThreads, 1) thin_step_chunked_pipe_kernel(ThinArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char cpm[];
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kTmaThreads, 1) thin_step_tma_kernel(ThinArgs<T> a, const __grid_constant__ TensorMap map_x,
+                                                                       const __grid_constant__ TensorMap map_s) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    __shared__ __align__(8) unsigned long long full_bar[kTmaStages], empty_bar[kTmaStages];
+    constexpr int KS = TmaSlab<T>::K;
     const int d = a.kp.d;
-    constexpr int kArr = DENSE ? 3 : 2;
-    T* ysh = reinterpret_cast<T*>(cpm);
+    // [1024-byte aligned] kTmaStages x { x tile, s tile } | y[d] sy[d]
+    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tsm) + 1023u) & ~(uintptr_t)1023u);
+    T* ysh = reinterpret_cast<T*>(tiles + (size_t)kTmaStages * 2 * kTmaTileBytes);
     T* sysh = ysh + d;
-    T* ylsh = sysh + d;
-    T* ring = ylsh + d;                                       // NST x { xt, st, (xlt) } of kThreads x kChunkLd
 
     const Cand win = pick_winner(a);
     if (!winner_ok(win)) return;                 // job aborted (block-uniform): nothing is read, nothing is published
     const long long sel = (long long)win.i;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.idx_out[a.step - 1] = (uint32_t)sel;
-    for (int k = threadIdx.x; k < d; k += kThreads) {
+    for (int k = threadIdx.x; k < d; k += kTmaThreads) {
         ysh[k] = __ldg(a.x + sel * d + k);
         sysh[k] = __ldg(a.s + sel * d + k);
-        ylsh[k] = DENSE ? __ldg(a.xl + sel * d + k) : T(0);
     }
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < kTmaStages; ++st) {
+            dev_mbar_init(&full_bar[st], 1);                     // the producer's arrive.expect_tx
+            dev_mbar_init(&empty_bar[st], kTmaRows / 32);        // one arrival per consumer warp
+        }
+        dev_mbar_fence_init();
+    }
+    __syncthreads();                                         // barriers initialised, y row visible
+
     const YWeight<T> yw = load_yweight<T, STRICT>(a, sel);
     const long long rows = a.row_end - a.row_begin;
-    const long long stride = (long long)gridDim.x * kThreads;
-    const long long first = (long long)blockIdx.x * kThreads;
+    const long long stride = (long long)gridDim.x * kTmaRows;
+    const long long first = (long long)blockIdx.x * kTmaRows;
     const long long ntiles = first < rows ? (rows - first + stride - 1) / stride : 0;
-    const int nslabs = (d + kChunkK - 1) / kChunkK;
+    const int nslabs = (d + KS - 1) / KS;
     const long long nstages = ntiles * nslabs;
     const int d8 = d - (d % 8);
-    const int kk = threadIdx.x % kChunkK, rr0 = threadIdx.x / kChunkK;
-
-    auto issue = [&](long long q) {
-        const long long it = q / nslabs;
-        const int k0 = (int)(q - it * nslabs) * kChunkK;
-        const int kc = min(kChunkK, d - k0);
-        const long long base = first + it * stride;
-        const int tile_rows = (int)min((long long)kThreads, rows - base);
-        T* xt = ring + (size_t)(q % NST) * kArr * kThreads * kChunkLd;
-        T* st = xt + kThreads * kChunkLd;
-        T* xlt = st + kThreads * kChunkLd;
-        const long long g0 = (a.row_begin + base + rr0) * d + k0 + kk;
-#pragma unroll
-        for (int j = 0; j < kChunkK; ++j) {
-            const int r = rr0 + j * (kThreads / kChunkK);
-            const bool ok = (kk < kc) && (r < tile_rows);
-            const long long g = g0 + (long long)j * (kThreads / kChunkK) * d;
-            if (ok) {
-                cp_async8(xt + r * kChunkLd + kk, a.x + g);
-                cp_async8(st + r * kChunkLd + kk, a.s + g);
-                if (DENSE) cp_async8(xlt + r * kChunkLd + kk, a.xl + g);
-            } else {
-                xt[r * kChunkLd + kk] = T(0);
-                st[r * kChunkLd + kk] = T(0);
-                if (DENSE) xlt[r * kChunkLd + kk] = T(0);
-            }
-        }
-    };
-
-    for (int q = 0; q < NST - 1; ++q) {                       // prologue: NST - 1 slabs in flight
-        if (q < nstages) issue(q);
-        cp_async_commit_group();                              // (possibly empty) keeps the group count uniform
-    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double bv = __longlong_as_double(0x7ff0000000000000LL);
     unsigned bi = 0xffffffffu;
-    ChunkRow<T, STRICT, DENSE> row;
-    row.reset();
-    for (long long q = 0; q < nstages; ++q) {
-        if (q + NST - 1 < nstages) issue(q + NST - 1);        // refills the buffer consumed in iteration q - 1
-        cp_async_commit_group();
-        cp_async_wait_group<NST - 1>();                       // slab q has landed (this thread's copies)
-        __syncthreads();                                      // ... and everybody else's; y row visible on the first pass
-        const long long it = q / nslabs;
-        const int slab = (int)(q - it * nslabs);
-        const int k0 = slab * kChunkK;
-        const int kc = min(kChunkK, d - k0);
-        const long long base = first + it * stride;
-        const int tile_rows = (int)min((long long)kThreads, rows - base);
-        const bool active = (int)threadIdx.x < tile_rows;
-        const T* xt = ring + (size_t)(q % NST) * kArr * kThreads * kChunkLd;
-        const T* st = xt + kThreads * kChunkLd;
-        const T* xlt = st + kThreads * kChunkLd;
-        if (active) {
-            if (slab == 0) row.reset();
-            row.slab(xt + threadIdx.x * kChunkLd, st + threadIdx.x * kChunkLd, xlt + threadIdx.x * kChunkLd, ysh, sysh,
-                     ylsh, k0, kc, d, d8, a.kp);
-            if (slab == nslabs - 1) {
-                const long long li = base + threadIdx.x;
-                const long long i = a.row_begin + li;
-                double k = row.value(d, d8, a.kp);
-                double v;
-                const double av = a.A[li];
-                if constexpr (STRICT) {
-                    if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, yw), k);
-                    v = __dadd_rn(av, __dmul_rn(2.0, k));
-                } else {
-                    v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, yw), k, av) : fma(2.0, k, av);
-                }
-                a.A[li] = v;
-                if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
+
+    if (warp == kTmaRows / 32) {
+        // ---- producer warp: one elected lane keeps the ring full ----------------------------------------------
+        if (lane == 0) {
+            for (long long q = 0; q < nstages; ++q) {
+                const int st = (int)(q % kTmaStages);
+                const long long use = q / kTmaStages;                       // how often this buffer was filled before
+                if (use > 0) dev_mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1));   // its previous contents are consumed
+                const long long it = q / nslabs;
+                const int k0 = (int)(q - it * nslabs) * KS;
+                const long long row0 = a.row_begin + first + it * stride;       // global row of the tile's first row
+                unsigned char* xt = tiles + (size_t)st * 2 * kTmaTileBytes;
+                dev_mbar_arrive_expect_tx(&full_bar[st], 2u * (unsigned)kTmaTileBytes);
+                dev_tma_load_2d(xt, &map_x, k0, (int)row0, &full_bar[st]);
+                dev_tma_load_2d(xt + kTmaTileBytes, &map_s, k0, (int)row0, &full_bar[st]);
             }
         }
-        __syncthreads();                                      // buffer q % NST may be overwritten by the next issue
+        __syncwarp();
+    } else {
+        // ---- consumer warps: thread per row -----------------------------------------------------------------
+        ChunkRow<T, STRICT, false> row;
+        row.reset();
+        const unsigned r7 = threadIdx.x & 7u;
+        for (long long q = 0; q < nstages; ++q) {
+            const int st = (int)(q % kTmaStages);
+            dev_mbar_wait(&full_bar[st], (unsigned)((q / kTmaStages) & 1));          // both tiles of slab q have landed
+            const long long it = q / nslabs;
+            const int slab = (int)(q - it * nslabs);
+            const int k0 = slab * KS;
+            const int kc = min(KS, d - k0);
+            const long long base = first + it * stride;
+            const int tile_rows = (int)min((long long)kTmaRows, rows - base);
+            const unsigned char* xt = tiles + (size_t)st * 2 * kTmaTileBytes;
+            if ((int)threadIdx.x < tile_rows) {
+                const SwizzledRow<T> xr{xt + (size_t)threadIdx.x * kTmaRowBytes, r7};
+                const SwizzledRow<T> sr{xt + kTmaTileBytes + (size_t)threadIdx.x * kTmaRowBytes, r7};
+                if (slab == 0) row.reset();
+                row.slab(xr, sr, xr, ysh, sysh, ysh, k0, kc, d, d8, a.kp);
+                if (slab == nslabs - 1) {
+                    const long long li = base + threadIdx.x;
+                    const long long i = a.row_begin + li;
+                    double k = row.value(d, d8, a.kp);
+                    double v;
+                    const double av = a.A[li];
+                    if constexpr (STRICT) {
+                        if (a.lw) k = __dmul_rn(weight_pair<T, STRICT>(a, i, yw), k);
+                        v = __dadd_rn(av, __dmul_rn(2.0, k));
+                    } else {
+                        v = a.lw ? fma(2.0 * weight_pair<T, STRICT>(a, i, yw), k, av) : fma(2.0, k, av);
+                    }
+                    a.A[li] = v;
+                    if (cand_better(v, (unsigned)i, bv, bi)) { bv = v; bi = (unsigned)i; }
+                }
+            }
+            __syncwarp();                                                    // every lane is done with buffer st
+            if (lane == 0) dev_mbar_arrive(&empty_bar[st]);
+        }
     }
     grid_argmin_publish(bv, bi, a);
 }
@@ -1461,15 +1515,57 @@ static int tiled_config(int d, bool dense, int& threads, size_t& smem) {
     return GFK_EUNSUPPORTED;
 }
 
-constexpr int kPipeStages = 3;
 template <typename T>
-static size_t chunk_pipe_smem(int d, bool dense) {
-    return sizeof(T) * (size_t)(3 * d + kPipeStages * (dense ? 3 : 2) * kThreads * kChunkLd);
+static size_t step_tma_smem(int d) {
+    return 1024 + (size_t)kTmaStages * 2 * kTmaTileBytes + sizeof(T) * 2 * (size_t)d;
+}
+
+// 2-D tensor map over a row-major (n, d) array: box = [128 bytes of dims] x [kTmaRows rows], SWIZZLE_128B,
+// out-of-bounds elements read as zero.  false: the driver entry point is missing or refused the layout.
+template <typename T>
+static bool make_step_tensor_map(TensorMap* map, const T* base, long long n, int d) {
+#if defined(GFK_SIMT_HOST)
+    memset(map, 0, sizeof(*map));
+    map->magic = 0x7a3du;
+    map->elem = (unsigned)sizeof(T);
+    map->box0 = (unsigned)TmaSlab<T>::K;
+    map->box1 = (unsigned)kTmaRows;
+    map->swizzle = 128;
+    map->base = base;
+    map->dim0 = (unsigned long long)d;
+    map->dim1 = (unsigned long long)n;
+    map->stride1 = (unsigned long long)d * sizeof(T);
+    return true;
+#else
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(T)};
+    const cuuint32_t box[2] = {(cuuint32_t)TmaSlab<T>::K, (cuuint32_t)kTmaRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return encode(map, dt, 2, const_cast<T*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+#endif
 }
 
 template <typename T, bool STRICT>
 static int launch_step(const ThinArgs<T>& a, int d, cudaStream_t st, int grid_small, int grid_tiled,
-                       int tiled_threads, size_t tiled_smem) {
+                       int tiled_threads, size_t tiled_smem, const TensorMap* maps) {
     const bool dense = a.xl != nullptr;
     if (!dense && d == 2) {
         thin_step_small_kernel<T, 2, STRICT, 4><<<grid_small, kThreads, 0, st>>>(a);
@@ -1480,9 +1576,7 @@ static int launch_step(const ThinArgs<T>& a, int d, cudaStream_t st, int grid_sm
     } else if (!dense && d == 3) {
         thin_step_small_kernel<T, 3, STRICT, 2><<<grid_small, kThreads, 0, st>>>(a);
     } else if (tiled_threads == -1) {
-        const size_t smem = chunk_pipe_smem<T>(d, dense);
-        if (dense) thin_step_chunked_pipe_kernel<T, STRICT, !STRICT, kPipeStages><<<grid_tiled, kThreads, smem, st>>>(a);
-        else thin_step_chunked_pipe_kernel<T, STRICT, false, kPipeStages><<<grid_tiled, kThreads, smem, st>>>(a);
+        thin_step_tma_kernel<T, STRICT><<<grid_tiled, kTmaThreads, step_tma_smem<T>(d), st>>>(a, maps[0], maps[1]);
     } else if (tiled_threads == 0) {
         const size_t smem = sizeof(T) * (size_t)(3 * d + (dense ? 3 : 2) * kThreads * kChunkLd);
         if (dense) thin_step_chunked_kernel<T, STRICT, !STRICT><<<grid_tiled, kThreads, smem, st>>>(a);
@@ -1641,17 +1735,19 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     // whole row at once) or y rows too long for its shared memory -> the row-tiled kernel
     const size_t chunked_smem = sizeof(T) * (size_t)(3 * d + (a.xl ? 3 : 2) * kThreads * kChunkLd);
     const bool use_chunked = uses_tiled && !(STRICT && d > 128) && chunked_smem <= 200 * 1024;
+    // TMA-fed step kernel (opt-in): scalar preconditioner, rows a multiple of 16 bytes (the tensor-map stride rule)
     bool use_pipe = false;
-    if (const char* penv = getenv("GFK_CHUNK_PIPE")) {
-        use_pipe = penv[0] == '1' && uses_tiled && use_chunked && chunk_pipe_smem<T>(d, a.xl != nullptr) <= 220 * 1024;
+    TensorMap maps[2];
+    if (const char* penv = getenv("GFK_STEP_TMA")) {
+        use_pipe = penv[0] == '1' && uses_tiled && use_chunked && a.xl == nullptr && ((size_t)d * sizeof(T)) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(a.x) % 16 == 0 && reinterpret_cast<uintptr_t>(a.s) % 16 == 0 &&
+                   a.n < 0x7fffffffLL && step_tma_smem<T>(d) <= 220 * 1024 &&
+                   make_step_tensor_map<T>(&maps[0], a.x, a.n, d) && make_step_tensor_map<T>(&maps[1], a.s, a.n, d);
     }
     if (use_pipe) {
-        const size_t psm = chunk_pipe_smem<T>(d, a.xl != nullptr);
-        if (a.xl) GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_pipe_kernel<T, STRICT, !STRICT, kPipeStages>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-        else GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_pipe_kernel<T, STRICT, false, kPipeStages>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-        tiled_threads = -1;                          // launch_step: the pipelined kernel
+        GFK_CUDA(cudaFuncSetAttribute(thin_step_tma_kernel<T, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)step_tma_smem<T>(d)));
+        tiled_threads = -1;                          // launch_step: the TMA-fed kernel
     } else if (uses_tiled && use_chunked) {
         if (a.xl) GFK_CUDA(cudaFuncSetAttribute(thin_step_chunked_kernel<T, STRICT, !STRICT>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunked_smem));
@@ -1679,7 +1775,7 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     const int grid_init = grid_for(kThreads, 8);
     const int grid_small = grid_for(kThreads * 2, 4);
     const int grid_tiled = !uses_tiled ? 1
-                           : use_pipe ? grid_for(kThreads, 1)
+                           : use_pipe ? grid_for(kTmaRows, 1)
                            : use_chunked ? grid_for(kThreads, chunked_smem > 72 * 1024 ? 2 : 3)
                                          : grid_for(tiled_threads, tiled_smem > 50 * 1024 ? 2 : 4);
 
@@ -1696,7 +1792,7 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
         }
         a.step = step;                           // consumes exchange step-1, produces exchange step
         if (step == m) break;
-        launch_step<T, STRICT>(a, d, st, grid_small, grid_tiled, tiled_threads, tiled_smem);
+        launch_step<T, STRICT>(a, d, st, grid_small, grid_tiled, tiled_threads, tiled_smem, maps);
     }
     thin_finish_kernel<T><<<1, 32, 0, st>>>(a);
     count_launches(2 + (long long)m);   // reset + init + (m - 1) steps + finish

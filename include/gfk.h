@@ -101,6 +101,15 @@ size_t gfk_median_ws_bytes(int64_t n, int32_t cap);
 int gfk_median_pdist(const double* x, int64_t n, int32_t d, int32_t cap, double* mid_host,
                      void* ws, void* stream);
 
+/* ---- a2: stein_thinning.kernel.make_precon, 'smpcov' (never called by the reference; parity unpinned) ----------
+ * gfk_covariance: cov_host (d x d doubles, host) <- np.cov(x, rowvar=False) (ddof = 1) of the device sample, summed
+ * in fixed 2048-row chunks.  SYNCHRONOUS.  ws: gfk_covariance_ws_bytes(n, d) bytes of device scratch.
+ * gfk_rows_times_matrix: out (n, d) <- x (n, d) @ L (d, d row-major, device), the `xl` array of gfk_problem for a
+ * dense symmetric preconditioner L.  Asynchronous.  1 <= d <= 160. */
+size_t gfk_covariance_ws_bytes(int64_t n, int32_t d);
+int gfk_covariance(const double* x, int64_t n, int32_t d, double* cov_host, void* ws, void* stream);
+int gfk_rows_times_matrix(const double* x, int64_t n, int32_t d, const double* L, double* out, void* stream);
+
 /* float64 -> float32 copy of a device array (count elements), for GFK_F32_FAST */
 int gfk_to_f32(const double* src, float* dst, int64_t count, void* stream);
 
@@ -177,8 +186,11 @@ int gfk_energy_distance_cumulative(const double* x, int64_t n, const double* y, 
  *   ws        : device scratch of gfk_thin_ws_bytes() bytes
  * Asynchronous on `stream`. */
 size_t gfk_thin_ws_bytes(void);
-/* SYNCHRONOUS: after gfk_thin on the same stream and workspace - non-zero if the single-launch kernel abandoned an
- * exchange (a block or a peer rank never arrived within the spin limit); idx_out is then invalid */
+/* SYNCHRONOUS: after gfk_thin on the same stream and workspace - GFK_ECUDA if the job aborted on the device: a wait
+ * for another block or a peer rank ran past its deadline (GFK_SPIN_MS, default 200 ms; first cross-rank exchange
+ * GFK_SPIN_FIRST_MS, default 5000 ms), a peer rank aborted and said so, or an exchanged row index was out of range.
+ * Every rank of the job gets the error within one deadline; idx_out is then invalid.  An empty shard
+ * (row_begin == row_end, more ranks than rows) is legal on a multi-rank communicator. */
 int gfk_thin_check(const void* ws, void* stream);
 int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end, int32_t m,
              double* objective, uint32_t* idx_out, void* ws, void* stream);
@@ -208,7 +220,9 @@ int gfk_comm_init(int n_ranks, int rank, const void* id128_host, const char* ncc
  * gfk_p2p_local_handle (64-byte cudaIpcMemHandle_t out), the handles are all-gathered out of band into
  * handles_host[n_ranks * 64], then every rank calls gfk_p2p_open.  Afterwards gfk_thin exchanges its
  * (value, index) pairs with flag-in-data stores into the peers' mailboxes from inside the thinning kernels
- * (and the single-launch persistent kernel becomes available on every rank); without it NCCL all-gather is used. */
+ * (and the single-launch persistent kernel becomes available on every rank).  OPT-IN PER JOB: gfk_thin uses the
+ * mailboxes only when they are open AND the environment of the calling process has GFK_P2P=1 (the same on every
+ * rank); the default multi-rank exchange is a 16-byte ncclAllGather per greedy step. */
 int gfk_p2p_local_handle(void* handle64_host);
 int gfk_p2p_open(const void* handles_host, int n_ranks, int rank);
 int gfk_p2p_enabled(void);

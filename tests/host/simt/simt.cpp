@@ -93,6 +93,9 @@ struct Block {
     const std::function<void()>* fn = nullptr;
     bool failed = false;
     unsigned polls = 0;
+    struct PendingTma { void* dst; TensorMap2D map; int c0, c1; unsigned long long* bar; };
+    std::vector<PendingTma> tma;        // bulk tensor copies issued and not yet completed
+    unsigned long long mbar_polls = 0;  // consecutive unsuccessful mbarrier tests (a wait that can never complete)
     std::vector<unsigned> tmem;         // 128 lanes x 512 columns once allocated
     int tmem_cols = 0;                  // allocated columns (0: none)
     const char* site_file = nullptr;   // call site of the __syncthreads being collected
@@ -309,6 +312,107 @@ void cp_async_wait(int allow_pending_groups) {
     }
 }
 
+static std::atomic<long long> g_tma_loads{0};
+// ---- mbarrier: [63] phase, [62:48] pending arrivals, [47:32] arrival count of a phase, [31:0] pending bytes (signed) ----
+namespace {
+struct Mbar {
+    unsigned phase, pending, count;
+    int tx;
+};
+Mbar mbar_unpack(unsigned long long v) {
+    return Mbar{(unsigned)(v >> 63), (unsigned)((v >> 48) & 0x7fffu), (unsigned)((v >> 32) & 0xffffu), (int)(unsigned)(v & 0xffffffffu)};
+}
+unsigned long long mbar_pack(const Mbar& m) {
+    return ((unsigned long long)m.phase << 63) | ((unsigned long long)(m.pending & 0x7fffu) << 48) |
+           ((unsigned long long)(m.count & 0xffffu) << 32) | (unsigned long long)(unsigned)m.tx;
+}
+void mbar_settle(unsigned long long* bar, Mbar m) {
+    if (m.pending == 0 && m.tx == 0) { m.phase ^= 1u; m.pending = m.count; }     // the phase completes
+    *bar = mbar_pack(m);
+}
+}  // namespace
+
+void mbar_init(unsigned long long* bar, int count) {
+    check_align(bar, 8, "mbarrier.init");
+    if (count < 1 || count > 0x7fff) fail("mbarrier.init with count %d", count);
+    *bar = mbar_pack(Mbar{0u, (unsigned)count, (unsigned)count, 0});
+}
+
+void mbar_arrive(unsigned long long* bar) {
+    Mbar m = mbar_unpack(*bar);
+    if (m.count == 0) fail("mbarrier.arrive on an uninitialised barrier");
+    if (m.pending == 0) fail("mbarrier.arrive: more arrivals than the barrier's count in one phase");
+    m.pending--;
+    mbar_settle(bar, m);
+    if (random_sched()) { Block* b = t_blk; b->running->wait = W_NONE; yield_to_scheduler(b, b->running); }
+}
+
+void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    Mbar m = mbar_unpack(*bar);
+    if (m.count == 0) fail("mbarrier.arrive.expect_tx on an uninitialised barrier");
+    if (m.pending == 0) fail("mbarrier.arrive.expect_tx: more arrivals than the barrier's count in one phase");
+    m.tx += (int)bytes;
+    m.pending--;
+    mbar_settle(bar, m);
+}
+
+static void tma_complete_all(Block* b) {
+    std::vector<Block::PendingTma> todo;
+    todo.swap(b->tma);
+    for (const Block::PendingTma& t : todo) {
+        const TensorMap2D& mp = t.map;
+        const size_t row_bytes = (size_t)mp.box0 * mp.elem;
+        for (unsigned j = 0; j < mp.box1; ++j) {
+            for (unsigned i = 0; i < mp.box0; ++i) {
+                const long long g0 = (long long)t.c0 + i, g1 = (long long)t.c1 + j;
+                size_t off = (size_t)j * row_bytes + (size_t)i * mp.elem;
+                if (mp.swizzle == 128) off ^= ((off >> 7) & 7u) << 4;
+                char* d = static_cast<char*>(t.dst) + off;
+                if (g0 >= 0 && g1 >= 0 && (unsigned long long)g0 < mp.dim0 && (unsigned long long)g1 < mp.dim1)
+                    memcpy(d, static_cast<const char*>(mp.base) + (size_t)g1 * mp.stride1 + (size_t)g0 * mp.elem, mp.elem);
+                else
+                    memset(d, 0, mp.elem);                       // out-of-bounds elements are zero-filled
+            }
+        }
+        Mbar m = mbar_unpack(*t.bar);
+        m.tx -= (int)(row_bytes * mp.box1);                      // the whole box counts, in bounds or not
+        mbar_settle(t.bar, m);
+    }
+}
+
+bool mbar_test(unsigned long long* bar, unsigned parity) {
+    Block* b = t_blk;
+    tma_complete_all(b);
+    const Mbar m = mbar_unpack(*bar);
+    if (m.count == 0) fail("mbarrier.try_wait on an uninitialised barrier");
+    const bool done = m.phase != (parity & 1u);       // the phase with this parity has completed
+    if (done) b->mbar_polls = 0;
+    else if (++b->mbar_polls > 400000000ull) fail("mbarrier wait never completes (missing arrive / expect_tx?)");
+    return done;
+}
+
+void tma_load_2d(void* dst, const TensorMap2D* map, int c0, int c1, unsigned long long* bar) {
+    Block* b = t_blk;
+    if (!map || map->magic != 0x7a3du) fail("cp.async.bulk.tensor with something that is not a tensor map");
+    if (map->elem == 0 || (map->box0 * map->elem) % 16 != 0 || map->box0 > 256 || map->box1 > 256 || map->stride1 % 16 != 0 ||
+        reinterpret_cast<uintptr_t>(map->base) % 16 != 0)
+        fail("cp.async.bulk.tensor: tensor map violates the TMA alignment rules");
+    if (map->swizzle == 128) {
+        if (map->box0 * map->elem > 128) fail("cp.async.bulk.tensor: SWIZZLE_128B needs an inner box of at most 128 bytes");
+        check_align(dst, 1024, "cp.async.bulk.tensor destination (SWIZZLE_128B)");
+    } else {
+        check_align(dst, 128, "cp.async.bulk.tensor destination");
+    }
+    const size_t bytes = (size_t)map->box0 * map->elem * map->box1;
+    if (static_cast<char*>(dst) < b->smem) fail("cp.async.bulk.tensor destination outside dynamic shared memory");
+    g_tma_loads.fetch_add(1, std::memory_order_relaxed);
+    memset(dst, 0xff, bytes);                                    // not there yet: a reader that does not wait sees NaNs
+    b->tma.push_back(Block::PendingTma{dst, *map, c0, c1, bar});
+}
+
+}  // namespace simt
+extern "C" long long simt_tma_loads() { return simt::g_tma_loads.load(); }   // tests: did the TMA kernel run at all?
+namespace simt {
 unsigned long long now_ns() {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -387,6 +491,8 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
     b.warps.assign((size_t)nwarps, WarpState());
     for (NamedBarrier& nb : b.named) nb = NamedBarrier();
     b.tmem_cols = 0;
+    b.tma.clear();
+    b.mbar_polls = 0;
     if (smem_bytes) memset(b.smem, 0xff, smem_bytes);   // poison: NaN patterns / huge integers
     uint3 bid;
     bid.x = linear_block % grid.x;
@@ -456,6 +562,10 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
         b.running = &f;
         simt_switch(&b.sched_sp, f.sp);
         b.running = nullptr;
+    }
+    if (!b.failed && !b.tma.empty()) {
+        record_error("block exited with cp.async.bulk.tensor copies in flight (nobody waited for their mbarrier)");
+        b.tma.clear();
     }
     if (!b.failed && b.tmem_cols) {
         record_error("block exited without tcgen05.dealloc: tensor memory would stay allocated on the SM");

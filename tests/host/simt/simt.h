@@ -32,6 +32,7 @@
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static thread_local
+#define __grid_constant__
 
 // ---- vector types ------------------------------------------------------------------------------------------
 struct uint3 { unsigned x, y, z; };
@@ -75,6 +76,26 @@ void cp_async_commit();
 void cp_async_wait(int allow_pending_groups);
 [[noreturn]] void fail(const char* fmt, ...);
 void check_align(const void* p, size_t a, const char* what);
+
+// ---- mbarrier + TMA (cp.async.bulk.tensor.2d) model ------------------------------------------------------------
+// What the emulator's stand-in for cuTensorMapEncodeTiled fills in: a 2-D row-major tensor of `elem`-byte elements,
+// dim0 fastest, rows stride1 bytes apart; loads move a box0 x box1 box, out-of-bounds elements read as zero,
+// swizzle = 128: CU_TENSOR_MAP_SWIZZLE_128B (16-byte chunk index XOR (128-byte row index mod 8)).
+struct __attribute__((aligned(64))) TensorMap2D {
+    unsigned magic;
+    unsigned elem, box0, box1, swizzle;
+    const void* base;
+    unsigned long long dim0, dim1, stride1;
+    char pad[128 - 56];
+};
+static_assert(sizeof(TensorMap2D) == 128, "same size as CUtensorMap");
+// an mbarrier object is the 8 bytes in shared memory it is on the device; a copy issued by tma_load_2d stays pending
+// (its destination poisoned) until some thread of the block next tests a barrier, then completes and reports its bytes
+void mbar_init(unsigned long long* bar, int count);
+void mbar_arrive(unsigned long long* bar);
+void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes);
+bool mbar_test(unsigned long long* bar, unsigned parity);
+void tma_load_2d(void* dst, const TensorMap2D* map, int c0, int c1, unsigned long long* bar);
 
 // grid x block fibers run fn(); cooperative: all blocks concurrently
 void launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& fn);
@@ -153,6 +174,8 @@ inline T __shfl_sync(unsigned mask, T v, int src_lane) {
     if (!((simt::warp_alive_mask() >> src) & 1u)) return v;
     return simt::from_bits<T>(all[src]);
 }
+// warp barrier: a rendezvous of the warp's live lanes, like every other *_sync collective here
+inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)mask; (void)simt::warp_gather(0ull); }
 inline int __any_sync(unsigned mask, int pred) {
     (void)mask;
     const unsigned long long* all = simt::warp_gather(pred ? 1ull : 0ull);

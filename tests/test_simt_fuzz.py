@@ -77,11 +77,10 @@ def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fas
 @settings(max_examples=int(os.environ.get('GFK_FUZZ_EXAMPLES', '25')), derandomize='GFK_FUZZ_EXAMPLES' not in os.environ,
           deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(2, 400), d=st.integers(1, 40), m=st.integers(1, 300),
-       gf=st.booleans(), n_parts=st.integers(1, 4), precision=st.sampled_from(['f64', 'f64-fast']), ws=st.booleans(),
+       gf=st.booleans(), n_parts=st.integers(1, 4), precision=st.sampled_from(['f64', 'f64-fast']),
        sms=st.integers(1, 6))
-def test_ksd_of_a_selection_matches_oracle(seed, n, d, m, gf, n_parts, precision, ws, sms):
-    """Cumulative KSD of m selected rows (with repeats), the triangle dealt over 1-4 parts, tile and warp-specialised
-    kernels - against the oracle's ksd of the re-indexed integrand."""
+def test_ksd_of_a_selection_matches_oracle(seed, n, d, m, gf, n_parts, precision, sms):
+    """Cumulative KSD of m selected rows (with repeats), the triangle dealt over 1-4 parts - against the oracle's ksd of the re-indexed integrand."""
     rng = np.random.default_rng(seed)
     x = rng.standard_normal((n, d)) + rng.standard_normal(d)
     g = -(x - x.mean(0)) * (1.0 + 0.1 * np.arange(d))
@@ -89,7 +88,6 @@ def test_ksd_of_a_selection_matches_oracle(seed, n, d, m, gf, n_parts, precision
     log_q = log_p + np.sin(x[:, 0])
     sel = rng.integers(0, n, m)
     os.environ['SIMT_SMS'] = str(sms)
-    os.environ['GFK_KSD_WS'] = '1' if ws else '0'
     try:
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
@@ -102,8 +100,7 @@ def test_ksd_of_a_selection_matches_oracle(seed, n, d, m, gf, n_parts, precision
         want = os_.ksd(lambda a, b: ref(sel[a], sel[b]), m)
         np.testing.assert_allclose(p.ksd(sel=sel, n_parts=n_parts), want, rtol=1e-10)
     finally:
-        for k in ('SIMT_SMS', 'GFK_KSD_WS'):
-            os.environ.pop(k, None)
+        os.environ.pop('SIMT_SMS', None)
 
 
 @settings(max_examples=int(os.environ.get('GFK_FUZZ_EXAMPLES', '25')), derandomize='GFK_FUZZ_EXAMPLES' not in os.environ,

@@ -570,66 +570,87 @@ def test_config_c1_full_size_and_c2_prefix_through_the_emulator():
         os.environ.pop('SIMT_SMS', None)
 
 
-@pytest.mark.parametrize('d', [1, 4, 10, 32])
-def test_warp_specialised_ksd_kernel_equals_the_tile_kernel(d, monkeypatch):
-    """GFK_KSD_WS=1: producer warp + named-barrier ring (ksd_rowsum_ws_kernel) must give bit-identical row sums to
-    ksd_rowsum_kernel - same pair arithmetic, same summation order - for any thread schedule."""
+@pytest.mark.parametrize('d', [1, 4, 10, 32, 40])
+def test_ksd_row_sums_do_not_depend_on_the_thread_schedule(d):
+    """ksd_rowsum_kernel (float64: 4 x 2 pairs per thread, 512 threads; float32: 4 x 4, 256 threads) double-buffers the
+    column tiles with cp.async between two barriers per stage: its row sums must be bit-identical under any thread
+    schedule, for the whole triangle and for a selection dealt over two parts, and match the oracle's ksd."""
     rng = np.random.default_rng(8000 + d)
-    n = 330                                                # 6 row tiles: the ring of 3 buffers wraps
+    n = 330                                                # 6 row tiles
     x, g = _mcmc_like(rng, n, d, dup=0.1)
     log_p = -0.5 * np.sum(x ** 2, axis=1)
     log_q = log_p + np.sin(x[:, 0])
     sel = rng.integers(0, n, 200)
     for prec in ('f64', 'f32'):
         for gf in (False, True):
-            mk = (lambda: H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=prec)) if gf else \
-                 (lambda: H.SimProblem(x, g, preconditioner='med', precision=prec))
-            monkeypatch.delenv('GFK_KSD_WS', raising=False)
-            p = mk()
+            p = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=prec) if gf else \
+                H.SimProblem(x, g, preconditioner='med', precision=prec)
+            H.set_schedule(False)
             base, base_sel = p.ksd_rowsums(), p.ksd_rowsums(sel=sel, part=1, n_parts=2)
-            monkeypatch.setenv('GFK_KSD_WS', '1')
-            for random, seed in ((False, 0), (True, 1), (True, 2)):
-                H.set_schedule(random, seed)
+            for seed in (1, 2):
+                H.set_schedule(True, seed)
                 got, got_sel = p.ksd_rowsums(), p.ksd_rowsums(sel=sel, part=1, n_parts=2)
-                assert np.array_equal(got[0], base[0]) and np.array_equal(got[1], base[1]), (prec, gf, random, seed)
-                assert np.array_equal(got_sel[0], base_sel[0]), (prec, gf, random, seed)
+                assert np.array_equal(got[0], base[0]) and np.array_equal(got[1], base[1]), (prec, gf, seed)
+                assert np.array_equal(got_sel[0], base_sel[0]), (prec, gf, seed)
             H.set_schedule(False)
     ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med')
     np.testing.assert_allclose(H.SimProblem(x, g, log_p, log_q, preconditioner='med').ksd(), os_.ksd(ref, n), rtol=1e-10)
 
 
-@pytest.mark.parametrize('d', [5, 9, 17, 64])
-def test_pipelined_step_kernel_equals_the_slab_kernel(d, monkeypatch):
-    """GFK_CHUNK_PIPE=1: thin_step_chunked_pipe_kernel (three slabs in flight per CTA) must select the oracle's indices
-    and leave bit-identical objectives to thin_step_chunked_kernel, in every precision, under any thread schedule."""
+@pytest.mark.parametrize('d', [6, 10, 16, 18, 64, 100])
+def test_tma_fed_step_kernel_equals_the_slab_kernel(d, monkeypatch):
+    """GFK_STEP_TMA=1: thin_step_tma_kernel (a producer warp keeps three [256 rows] x [128 bytes] slabs of x and s in
+    flight with cp.async.bulk.tensor + mbarriers, SWIZZLE_128B tiles, eight consumer warps, thread per row) must select
+    the oracle's indices and leave bit-identical objectives to thin_step_chunked_kernel, in every precision, under any
+    thread schedule.  The emulator completes a bulk copy only when some thread next tests an mbarrier and poisons its
+    destination until then, so a consumer that does not wait for `full`, or a producer that does not wait for `empty`,
+    reads NaNs."""
     monkeypatch.setenv('GFK_PERSISTENT', '0')
-    monkeypatch.setenv('SIMT_SMS', '2')                          # 2 CTAs x 256 rows: several tiles per CTA
+    monkeypatch.setenv('SIMT_SMS', '2')                          # 2 CTAs x 256 rows: several tiles per CTA, ring wraps
     rng = np.random.default_rng(9000 + d)
     x, g = _mcmc_like(rng, 1100, d)
     log_p = -0.5 * np.sum(x ** 2, axis=1) / d
     log_q = log_p + 0.5 * np.sin(x[:, 0])
     m = 6
     expect = ot.thin_gf(x, log_p, log_q, g, m, preconditioner='med')
+    lib = H.load()
     for precision in ('f64', 'f64-fast', 'f32'):
-        monkeypatch.delenv('GFK_CHUNK_PIPE', raising=False)
+        monkeypatch.delenv('GFK_STEP_TMA', raising=False)
         base = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(m)
-        monkeypatch.setenv('GFK_CHUNK_PIPE', '1')
+        monkeypatch.setenv('GFK_STEP_TMA', '1')
         for random, seed in ((False, 0), (True, 5)):
             H.set_schedule(random, seed)
+            lib.simt_tma_loads.restype = ctypes.c_longlong
+            before = lib.simt_tma_loads()
             idx, obj = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision=precision).thin(m)
+            eligible = (d * (4 if precision == 'f32' else 8)) % 16 == 0       # the tensor-map stride rule
+            assert (lib.simt_tma_loads() > before) == eligible, 'TMA kernel ran / did not run against its eligibility rule'
             assert np.array_equal(idx, base[0]) and np.array_equal(obj, base[1]), (precision, random)
         H.set_schedule(False)
         if precision != 'f32':
             assert np.array_equal(base[0], expect), precision
-    # dense preconditioner: the pipelined kernel does not fit three 3-array slabs and must fall back, not fail
+    # score-based kernel (no weights) and a shard that starts in the middle of the sample
+    monkeypatch.delenv('GFK_STEP_TMA', raising=False)
+    p = H.SimProblem(x, g, preconditioner='med')
+    want = p.thin(5)
+    monkeypatch.setenv('GFK_STEP_TMA', '1')
+    got = p.thin(5)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert np.array_equal(got[0], ot.thin(x, g, 5, preconditioner='med'))
+    # dense preconditioner and odd d (rows not a multiple of 16 bytes): not eligible, must fall back, not fail
     a = rng.standard_normal((d, d))
     dense = a @ a.T / d + np.eye(d)
     p = H.SimProblem(x[:300], g[:300], preconditioner=dense, precision='f64-fast')
-    monkeypatch.delenv('GFK_CHUNK_PIPE', raising=False)
+    monkeypatch.delenv('GFK_STEP_TMA', raising=False)
     want = p.thin(4)
-    monkeypatch.setenv('GFK_CHUNK_PIPE', '1')
+    monkeypatch.setenv('GFK_STEP_TMA', '1')
+    before = lib.simt_tma_loads()
     got = p.thin(4)
+    assert lib.simt_tma_loads() == before
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    xo, go = _mcmc_like(rng, 700, d + 1)
+    assert np.array_equal(H.SimProblem(xo, go, preconditioner='med').thin(4)[0], ot.thin(xo, go, 4, preconditioner='med'))
+    assert lib.simt_tma_loads() == before
 
 
 def test_full_size_c3_on_the_b200_grid_shape(monkeypatch):

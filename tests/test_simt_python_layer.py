@@ -22,7 +22,7 @@ def api(monkeypatch):
     import types
     from gradient_free_mcmc_postprocessing_b200 import _engine, _lib, chains, kernel, proxies, stein, thinning
     from gradient_free_mcmc_postprocessing_b200.utils import ksd as uksd
-    for k in ('GFK_PERSISTENT', 'GFK_RESIDENT', 'SIMT_SMS', 'GFK_KSD_WS', 'GFK_PRECISION'):
+    for k in ('GFK_PERSISTENT', 'GFK_RESIDENT', 'SIMT_SMS', 'GFK_PRECISION'):
         monkeypatch.delenv(k, raising=False)
     H.set_schedule(False)
     monkeypatch.setattr(_lib, '_lib', H.load())

@@ -43,26 +43,23 @@ for n in (50_000, 200_000):
         p = SteinProblem(c['sample'], c['gradient_q'], log_p=c['log_p'], log_q=c['log_q'], preconditioner='med',
                          precision=prec)
         pairs = n * (n + 1) / 2
-        for ws in ('0', '1'):                        # 1: warp-specialised producer / consumer kernel (opt-in)
-            os.environ['GFK_KSD_WS'] = ws
-            ks = p.ksd(None, min(n, 20_000))
-            t = timed(lambda: p.ksd(None, n), reps=2)
-            note(f'ksd_c4:{n}:{prec}:ws{ws}', seconds=t, pair_evals_per_s=pairs / t,
-                 fp64_tflops_algorithmic=pairs * 99 / t / 1e12, ks_last=float(ks[-1]))
-        os.environ.pop('GFK_KSD_WS', None)
+        ks = p.ksd(None, min(n, 20_000))
+        t = timed(lambda: p.ksd(None, n), reps=2)
+        note(f'ksd_c4:{n}:{prec}', seconds=t, pair_evals_per_s=pairs / t,
+             fp64_tflops_algorithmic=pairs * 99 / t / 1e12, ks_last=float(ks[-1]))
     del p
 
-# C5-shaped step kernel (d = 64): slab kernel vs the opt-in three-stage cp.async pipeline
+# C5-shaped step kernel (d = 64): slab kernel vs the opt-in TMA-fed kernel (cp.async.bulk.tensor + mbarrier ring)
 c = synthetic.config_c5(n=500_000, m=40)
 for prec in ('f64', 'f64-fast', 'f32'):
     for pipe in ('0', '1'):
-        os.environ['GFK_CHUNK_PIPE'] = pipe
+        os.environ['GFK_STEP_TMA'] = pipe
         p = SteinProblem(c['sample'], c['gradient'], preconditioner='med', precision=prec)
         idx = p.thin(40)
         t = timed(lambda: p.thin(40), reps=2)
         note(f'c5_step:{prec}:pipe{pipe}', us_per_step=t / 40 * 1e6, hbm_floor_us=500_000 * (1040 if prec != 'f32' else 528) / 6547.2e3,
              idx_head=[int(v) for v in idx[:6]])
-    os.environ.pop('GFK_CHUNK_PIPE', None)
+    os.environ.pop('GFK_STEP_TMA', None)
 del p
 
 # section 8f kernels
