@@ -369,3 +369,34 @@ class SteinProblem:
             check(lib.gfk_pairs(ctypes.byref(self.struct), _ptr(a_dev), _ptr(b_dev), ia.size, _ptr(out),
                                 _stream_ptr(self.device)))
             return out.cpu().numpy().reshape(ia.shape)
+
+
+def thin_batched(problems, n_points):
+    """``[p.thin(n_points) for p in problems]`` in ONE cooperative launch (``gfk_thin_batched``: one group of CTAs per
+    chain), for independent single-rank problems on one device.  Returns ``None`` - nothing launched - when the set is
+    not eligible (d > 4, mixed kernel kinds or precisions, a dense preconditioner, a chain too long for its CTA
+    group); the caller then thins the chains one after the other."""
+    lib = _lib.load()
+    m = int(n_points)
+    if m < 1:
+        raise ValueError('n_points must be at least 1.')
+    n = len(problems)
+    if n == 0:
+        return []
+    device = problems[0].device
+    if any(p.device != device for p in problems) or lib.gfk_comm_size() != 1:
+        return None
+    with torch.cuda.device(device):
+        structs = (Problem * n)(*[p.struct for p in problems])
+        objectives = [torch.empty(p.n, dtype=torch.float64, device=device) for p in problems]
+        idx = [torch.empty(m, dtype=torch.int32, device=device) for _ in problems]
+        obj_ptrs = (ctypes.c_void_p * n)(*[o.data_ptr() for o in objectives])
+        idx_ptrs = (ctypes.c_void_p * n)(*[i.data_ptr() for i in idx])
+        ws = _bytes(lib.gfk_thin_batched_ws_bytes(n) + 256, device)
+        base = (ws.data_ptr() + 255) // 256 * 256
+        rc = lib.gfk_thin_batched(structs, n, m, obj_ptrs, idx_ptrs, ctypes.c_void_p(base), _stream_ptr(device))
+        if rc == _lib.GFK_EUNSUPPORTED:
+            return None
+        check(rc)
+        check(lib.gfk_thin_batched_check(ctypes.c_void_p(base), n, _stream_ptr(device)))
+        return [i.cpu().numpy().view(np.uint32) for i in idx]

@@ -67,6 +67,9 @@ PROTOTYPES = {
     'gfk_thin_ws_bytes': (_sz, []),
     'gfk_thin': (ctypes.c_int, [_pp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     'gfk_thin_check': (ctypes.c_int, [_vp, _vp]),
+    'gfk_thin_batched_ws_bytes': (_sz, [_i32]),
+    'gfk_thin_batched': (ctypes.c_int, [_pp, _i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp]),
+    'gfk_thin_batched_check': (ctypes.c_int, [_vp, _i32, _vp]),
     'gfk_ksd_rowsums': (ctypes.c_int, [_pp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'gfk_ksd_finish': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'gfk_kmat': (ctypes.c_int, [_pp, _vp, _i64, _vp, _vp]),

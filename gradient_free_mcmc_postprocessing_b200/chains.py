@@ -5,12 +5,17 @@ its ``@cached`` decorator (``code/src/utils/caching.py:72-73,100-101``: ``np.sav
 ``<function>_<i>.npy``; ``code/notebooks/lotka_volterra/Stein_thinning.ipynb#c15-#c17``: ``thin`` mapped over chains
 with joblib).  Chains are independent, so with a ``torch.distributed`` group they are dealt round-robin to the ranks
 with no data-path collective - unlike ``thin`` itself, which shards the ROWS of one chain.
+
+The chains a rank owns are thinned in ONE cooperative launch (``gfk_thin_batched``: the grid is split into one group
+of CTAs per chain, each with its own workspace and exchange slots), so a set of small chains pays the per-step
+latency floor of the greedy search once, not once per chain; sets the batched kernel does not cover (d > 4, a dense
+preconditioner, a chain too long for its CTA group) fall back to one job per chain.
 """
 import os
 
 import numpy as np
 
-from .thinning import thin, thin_gf
+from ._engine import SteinProblem, thin_batched
 
 
 def load_array(a):
@@ -30,6 +35,14 @@ def _my_chains(n_chains, rank, world):
     return [i for i in range(n_chains) if i % world == rank]
 
 
+def _thin_set(problems, n_points):
+    """Index vectors of the problems: one batched launch when eligible, otherwise one job after the other."""
+    out = thin_batched(problems, n_points) if len(problems) > 1 else None
+    if out is None:
+        out = [p.thin(n_points) for p in problems]
+    return out
+
+
 def thin_chains(samples, gradients, n_points, standardize=True, preconditioner='id', *, out_paths=None, rank=0,
                 world=1, precision=None, device=None):
     """``[thin(samples[i], gradients[i], n_points, ...) for i in chains]``; entries may be arrays or .npy paths.
@@ -37,11 +50,13 @@ def thin_chains(samples, gradients, n_points, standardize=True, preconditioner='
     if len(samples) != len(gradients):
         raise ValueError('samples and gradients must list the same chains')
     out = [None] * len(samples)
-    for i in _my_chains(len(samples), rank, world):
-        out[i] = thin(load_array(samples[i]), load_array(gradients[i]), n_points, standardize, preconditioner,
-                      precision=precision, device=device)
+    mine = _my_chains(len(samples), rank, world)
+    problems = [SteinProblem(load_array(samples[i]), load_array(gradients[i]), standardize=standardize,
+                             preconditioner=preconditioner, precision=precision, device=device) for i in mine]
+    for i, idx in zip(mine, _thin_set(problems, n_points)):
+        out[i] = idx
         if out_paths is not None:
-            save_indices(out_paths[i], out[i])
+            save_indices(out_paths[i], idx)
     return out
 
 
@@ -51,10 +66,12 @@ def thin_gf_chains(samples, log_ps, log_qs, gradient_qs, n_points, standardize=T
     if not (len(samples) == len(log_ps) == len(log_qs) == len(gradient_qs)):
         raise ValueError('all inputs must list the same chains')
     out = [None] * len(samples)
-    for i in _my_chains(len(samples), rank, world):
-        out[i] = thin_gf(load_array(samples[i]), load_array(log_ps[i]), load_array(log_qs[i]),
-                         load_array(gradient_qs[i]), n_points, standardize, preconditioner, range_cap,
-                         precision=precision, device=device)
+    mine = _my_chains(len(samples), rank, world)
+    problems = [SteinProblem(load_array(samples[i]), load_array(gradient_qs[i]), log_p=load_array(log_ps[i]),
+                             log_q=load_array(log_qs[i]), standardize=standardize, preconditioner=preconditioner,
+                             range_cap=range_cap, precision=precision, device=device) for i in mine]
+    for i, idx in zip(mine, _thin_set(problems, n_points)):
+        out[i] = idx
         if out_paths is not None:
-            save_indices(out_paths[i], out[i])
+            save_indices(out_paths[i], idx)
     return out

@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <type_traits>
+#include <vector>
 
 #if !defined(GFK_SIMT_HOST)
 #include <cuda.h>      // CUtensorMap and its enums only: cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint
@@ -1154,9 +1155,11 @@ constexpr int kPollPerLane = 5;                       // persistent grid <= 160 
 // either variant does not carry the other's code.
 // TM: passes [0, rpt_tm) of every thread's rows are parked in tensor memory (float64, d = 2 or 4), the next rpt_res
 // passes in shared memory, the rest streams through L2
+// cta / ncta: this CTA's index within, and the size of, the group of CTAs that runs job `a` - the whole grid for one
+// job per launch, one slice of it per chain in the batched launch (every chain has its own workspace and slots)
 template <typename T, int D, bool STRICT, bool MULTI, bool WDD, bool TM>
-__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res,
-                                                                             int rpt_tm) {
+__device__ __forceinline__ void thin_persistent_body(const ThinArgs<T>& a, int m, int rpt, int rpt_res, int rpt_tm,
+                                                     const unsigned cta, const unsigned ncta) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double sv[32];
     __shared__ unsigned si[32];
@@ -1164,15 +1167,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
     __shared__ int abort_sh;
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
-    const long long TT = (long long)gridDim.x * nthr;
-    const long long gt = (long long)blockIdx.x * nthr + tid;
+    const long long TT = (long long)ncta * nthr;
+    const long long gt = (long long)cta * nthr + tid;
     const long long rows = a.row_end - a.row_begin;
     // Row ownership: pass j < rpt - 1 gives thread g of the grid row j * TT + g (coalesced, every thread busy).  The
     // LAST pass is usually partial; dealing its rows to the first threads of the grid would hand whole CTAs one more
     // row per thread than others (measured: CTAs 0-29 of 148 finish C3's update ~1.9 us after the rest, and every step
     // waits for the slowest CTA).  Its rows are dealt round-robin over the CTAs instead, so all SMs carry the same load.
     const long long last_base = (long long)(rpt - 1) * TT;
-    const long long last_e = (long long)tid * gridDim.x + blockIdx.x;
+    const long long last_e = (long long)tid * ncta + cta;
     const long long i_last = a.row_begin + last_base + last_e;     // this thread's global row of the last pass
     const int slots = rpt * nthr;
     double* A_sh = reinterpret_cast<double*>(psm);
@@ -1261,7 +1264,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         {
             unsigned long long (*slots_ll)[4] = ws->ll[step & 1];
             const unsigned tag16 = (unsigned)(step + 1);
-            if (tid == 0) slot_store(slots_ll[blockIdx.x], tag16, bv, bi);
+            if (tid == 0) slot_store(slots_ll[cta], tag16, bv, bi);
             if (tid < 32) {
                 double wv = __longlong_as_double(0x7ff0000000000000LL);
                 unsigned wi = 0xffffffffu;
@@ -1270,7 +1273,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                 const unsigned long long limit = ws->spin_ns;
                 // the first cross-rank exchange absorbs the skew between the ranks' host threads
                 const unsigned long long limit_x = (MULTI && step == 0) ? ws->spin_first_ns : limit;
-                if (!MULTI || blockIdx.x == 0) {
+                if (!MULTI || cta == 0) {
                     // gather.  Single rank: warp 0 of EVERY CTA polls all per-CTA slots and reduces them itself
                     // (one store->load hop per step).  Multi rank: only CTA 0 gathers, then talks to the peers
                     // and re-publishes the global winner for the other CTAs (measured: fewer pollers on lines a
@@ -1280,7 +1283,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                     unsigned pending = 0;
 #pragma unroll
                     for (int q = 0; q < kPollPerLane; ++q)
-                        if (tid + 32u * q < gridDim.x) pending |= 1u << q;
+                        if (tid + 32u * q < ncta) pending |= 1u << q;
                     SpinDeadline dl;
 #pragma unroll 1
                     while (pending) {
@@ -1345,7 +1348,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
                         wi = 0u;                                   // never used: every thread leaves below
                     }
                     win_sh = wi;
-                    if (blockIdx.x == 0 && !dead) {
+                    if (cta == 0 && !dead) {
                         a.idx_out[step] = wi;
                         if (step == m - 1) { ws->send.v = wv; ws->send.i = wi; ws->recv[0] = ws->send; ws->step = (unsigned)m; }
                     }
@@ -1452,6 +1455,33 @@ __global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(Thi
         tmem_fence_after_sync();
         if (tid < 32) tmem_free_all(tmem_base_sh);
     }
+}
+
+template <typename T, int D, bool STRICT, bool MULTI, bool WDD, bool TM>
+__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_kernel(ThinArgs<T> a, int m, int rpt, int rpt_res,
+                                                                             int rpt_tm) {
+    thin_persistent_body<T, D, STRICT, MULTI, WDD, TM>(a, m, rpt, rpt_res, rpt_tm, blockIdx.x, gridDim.x);
+}
+
+// ---- several independent chains in ONE cooperative launch --------------------------
+// The reference thins the five chains of an experiment with five calls (joblib over chains,
+// code/notebooks/lotka_volterra/Stein_thinning.ipynb#c15-#c17).  A greedy step of a small chain is latency, not work
+// (C2-sized: ~3 us of exchange per 2.6 us of update), so five chains run one after the other pay the floor five
+// times.  Here the grid is split into one group of CTAs per chain; each group runs the single-launch loop above on its
+// own job, workspace and flag-in-data slots, and the groups never talk to each other.
+template <typename T>
+struct ThinBatchJob {
+    ThinArgs<T> a;
+    int rpt, rpt_res;
+};
+
+template <typename T, int D, bool STRICT, bool WDD>
+__global__ void __launch_bounds__(kPersistThreads, 1) thin_persistent_batched_kernel(const ThinBatchJob<T>* __restrict__ jobs,
+                                                                                     int ncta_per_chain, int m) {
+    const unsigned chain = blockIdx.x / (unsigned)ncta_per_chain;
+    const unsigned cta = blockIdx.x - chain * (unsigned)ncta_per_chain;
+    const ThinBatchJob<T> job = jobs[chain];
+    thin_persistent_body<T, D, STRICT, false, WDD, false>(job.a, m, job.rpt, job.rpt_res, 0, cta, (unsigned)ncta_per_chain);
 }
 
 // winner of the last exchange -> idx_out[m - 1]
@@ -1800,6 +1830,103 @@ static int thin_typed(const gfk_problem* p, int64_t row_begin, int64_t row_end, 
     return GFK_OK;
 }
 
+// ---- batched chains: host side -------------------------------------------------------------------------------
+constexpr size_t kBatchWsStride = (sizeof(ThinWs) + 255) / 256 * 256;
+
+template <typename T, int D, bool STRICT, bool WDD>
+static int thin_batched_go(const std::vector<ThinBatchJob<T>>& jobs, int ncta, int m, size_t smem, void* jobs_dev,
+                           cudaStream_t st) {
+    auto kernel = thin_persistent_batched_kernel<T, D, STRICT, WDD>;
+    if (persistent_prepare(kernel, kPersistThreads, smem) != cudaSuccess) {
+        set_error("gfk_thin_batched: the batched kernel does not fit this device (shared memory %zu bytes)", smem);
+        return GFK_EUNSUPPORTED;
+    }
+    GFK_CUDA(cudaMemcpyAsync(jobs_dev, jobs.data(), sizeof(ThinBatchJob<T>) * jobs.size(), cudaMemcpyHostToDevice, st));
+    MailArgs no_mail;
+    memset(&no_mail, 0, sizeof(no_mail));
+    for (const ThinBatchJob<T>& j : jobs)
+        thin_reset_kernel<<<1, 1024, 0, st>>>(j.a.ws, no_mail, spin_limit_ns(), spin_first_limit_ns());
+    const cudaError_t e = launch_cooperative(kernel, (unsigned)(jobs.size() * (size_t)ncta), kPersistThreads, smem, st,
+                                             static_cast<const ThinBatchJob<T>*>(jobs_dev), ncta, m);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(thin_persistent_batched_kernel)", __FILE__, __LINE__);
+    count_launches(1 + (long long)jobs.size());
+    return GFK_OK;
+}
+
+template <typename T, bool STRICT>
+static int thin_batched_typed(const gfk_problem* probs, int n_chains, int m, double* const* objectives,
+                              uint32_t* const* idx_outs, void* ws_raw, cudaStream_t st) {
+    int dev = 0, coop = 0, smem_optin = 0;
+    GFK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (!coop) { set_error("gfk_thin_batched: the device has no cooperative launch"); return GFK_EUNSUPPORTED; }
+    const int d = probs[0].d;
+    const bool wdd = probs[0].lw && probs[0].w;
+    long long max_rows = 0;
+    for (int c = 0; c < n_chains; ++c) max_rows = probs[c].n > max_rows ? probs[c].n : max_rows;
+    // one group of CTAs per chain, all groups the same size, one CTA per SM at most
+    long long ncta = sm_count() / n_chains;
+    const long long want = (max_rows + kPersistThreads - 1) / kPersistThreads;
+    if (ncta > want) ncta = want;
+    if (ncta > 32 * kPollPerLane) ncta = 32 * kPollPerLane;
+    if (ncta < 1) { set_error("gfk_thin_batched: more chains (%d) than SMs", n_chains); return GFK_EUNSUPPORTED; }
+    const long long TT = ncta * kPersistThreads;
+    const size_t budget = (size_t)smem_optin - 1024;
+    const size_t per_row_slot = 2 * (size_t)d * kPersistThreads * sizeof(T);
+    std::vector<ThinBatchJob<T>> jobs((size_t)n_chains);
+    size_t smem = 0;
+    char* ws_bytes = static_cast<char*>(ws_raw);
+    for (int c = 0; c < n_chains; ++c) {
+        const gfk_problem& p = probs[c];
+        ThinBatchJob<T>& j = jobs[(size_t)c];
+        j.a.x = static_cast<const T*>(p.x);
+        j.a.s = static_cast<const T*>(p.s);
+        j.a.lw = static_cast<const T*>(p.lw);
+        j.a.w = static_cast<const T*>(p.w);
+        j.a.xl = nullptr;
+        j.a.A = objectives[c];
+        j.a.row_begin = 0;
+        j.a.row_end = p.n;
+        j.a.n = p.n;
+        j.a.kp = KParams{p.lambda, p.lambda_sq, p.trace, p.c, p.d, false};
+        j.a.ws = reinterpret_cast<ThinWs*>(ws_bytes + (size_t)c * kBatchWsStride);
+        j.a.idx_out = idx_outs[c];
+        j.a.n_ranks = 1;
+        j.a.step = 0;
+        j.a.mail_enabled = 0;
+        int rpt = (int)((p.n + TT - 1) / TT);
+        if (rpt < 1) rpt = 1;
+        const size_t base = (size_t)rpt * kPersistThreads * (sizeof(double) + (p.lw ? sizeof(T) : 0));
+        if (base > budget) {
+            set_error("gfk_thin_batched: chain %d (n = %lld) does not fit the shared memory of its %lld CTAs", c,
+                      (long long)p.n, ncta);
+            return GFK_EUNSUPPORTED;
+        }
+        int rpt_res = (int)((budget - base) / per_row_slot);
+        if (rpt_res > rpt) rpt_res = rpt;
+        j.rpt = rpt;
+        j.rpt_res = rpt_res;
+        const size_t need = base + (size_t)rpt_res * per_row_slot;
+        smem = need > smem ? need : smem;
+    }
+    void* jobs_dev = ws_bytes + (size_t)n_chains * kBatchWsStride;
+    switch (d) {
+#define GFK_BATCH_CASE(DD)                                                                                              \
+        case DD:                                                                                                        \
+            return wdd ? thin_batched_go<T, DD, STRICT, true>(jobs, (int)ncta, m, smem, jobs_dev, st)                   \
+                       : thin_batched_go<T, DD, STRICT, false>(jobs, (int)ncta, m, smem, jobs_dev, st);
+        GFK_BATCH_CASE(1)
+        GFK_BATCH_CASE(2)
+        GFK_BATCH_CASE(3)
+        GFK_BATCH_CASE(4)
+#undef GFK_BATCH_CASE
+        default: break;
+    }
+    set_error("gfk_thin_batched: d = %d (the single-launch kernel covers d <= 4)", d);
+    return GFK_EUNSUPPORTED;
+}
+
 // exchange-only loop over the peer mailboxes: measures the per-step cost of the cross-GPU stage alone.
 // failed: 0 ok, otherwise a kAbort* code (a rank that gives up tells its peers, so all leave within one deadline)
 // or 0x100 for a record that arrived with the wrong content
@@ -1858,6 +1985,52 @@ extern "C" int gfk_p2p_selftest(int iters, double* us_per_exchange_host, void* s
 }
 
 extern "C" size_t gfk_thin_ws_bytes(void) { return sizeof(gfk::ThinWs); }
+
+extern "C" size_t gfk_thin_batched_ws_bytes(int32_t n_chains) {
+    if (n_chains < 1) return 0;
+    return (size_t)n_chains * (gfk::kBatchWsStride + (sizeof(gfk::ThinBatchJob<double>) + 255) / 256 * 256);
+}
+
+extern "C" int gfk_thin_batched(const gfk_problem* problems, int32_t n_chains, int32_t m, double* const* objectives,
+                                uint32_t* const* idx_outs, void* ws, void* stream) {
+    using namespace gfk;
+    GFK_REQUIRE(problems && objectives && idx_outs && ws, "gfk_thin_batched: NULL pointer argument");
+    GFK_REQUIRE(n_chains >= 1 && m >= 1, "gfk_thin_batched: need n_chains >= 1 and m >= 1");
+    GFK_REQUIRE(reinterpret_cast<uintptr_t>(ws) % 256 == 0, "gfk_thin_batched: ws must be 256-byte aligned");
+    for (int c = 0; c < n_chains; ++c) {
+        const gfk_problem& p = problems[c];
+        GFK_REQUIRE(p.x && p.s && objectives[c] && idx_outs[c], "gfk_thin_batched: NULL pointer in chain %d", c);
+        GFK_REQUIRE(p.n >= 1 && p.n <= 0xfffffffeLL, "gfk_thin_batched: chain %d: n out of range", c);
+        if (p.d != problems[0].d || p.mode != problems[0].mode || (p.lw != nullptr) != (problems[0].lw != nullptr) ||
+            (p.w != nullptr) != (problems[0].w != nullptr) || p.xl != nullptr) {
+            set_error("gfk_thin_batched: chains must share d, mode and kernel kind, with a scalar preconditioner");
+            return GFK_EUNSUPPORTED;
+        }
+        const size_t row_bytes = (size_t)p.d * (p.mode == GFK_F32_FAST ? sizeof(float) : sizeof(double));
+        const size_t al = row_bytes % 16 == 0 ? 16 : (row_bytes % 8 == 0 ? 8 : 4);
+        GFK_REQUIRE(reinterpret_cast<uintptr_t>(p.x) % al == 0 && reinterpret_cast<uintptr_t>(p.s) % al == 0,
+                    "gfk_thin_batched: chain %d: x and s must be %zu-byte aligned", c, al);
+        if (p.mode == GFK_F64_STRICT && p.lw && p.w)
+            GFK_REQUIRE(reinterpret_cast<uintptr_t>(p.w) % 16 == 0, "gfk_thin_batched: chain %d: w must be 16-byte aligned", c);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (problems[0].mode) {
+        case GFK_F64_STRICT: return thin_batched_typed<double, true>(problems, n_chains, m, objectives, idx_outs, ws, st);
+        case GFK_F64_FAST: return thin_batched_typed<double, false>(problems, n_chains, m, objectives, idx_outs, ws, st);
+        case GFK_F32_FAST: return thin_batched_typed<float, false>(problems, n_chains, m, objectives, idx_outs, ws, st);
+        default: set_error("gfk_thin_batched: unknown mode %d", problems[0].mode); return GFK_EINVAL;
+    }
+}
+
+extern "C" int gfk_thin_batched_check(const void* ws, int32_t n_chains, void* stream) {
+    using namespace gfk;
+    GFK_REQUIRE(ws && n_chains >= 1, "gfk_thin_batched_check: bad arguments");
+    for (int c = 0; c < n_chains; ++c) {
+        const int rc = gfk_thin_check(static_cast<const char*>(ws) + (size_t)c * kBatchWsStride, stream);
+        if (rc != GFK_OK) return rc;
+    }
+    return GFK_OK;
+}
 
 extern "C" int gfk_thin_check(const void* ws, void* stream) {
     using namespace gfk;

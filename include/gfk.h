@@ -195,6 +195,26 @@ int gfk_thin_check(const void* ws, void* stream);
 int gfk_thin(const gfk_problem* p, int64_t row_begin, int64_t row_end, int32_t m,
              double* objective, uint32_t* idx_out, void* ws, void* stream);
 
+/* ---- next: several independent chains in one launch ------------------------------------------------
+ * Reference: thin() mapped over the five chains of an experiment with joblib
+ * (code/notebooks/lotka_volterra/Stein_thinning.ipynb#c15-#c17; code/src/utils/parallel.py:48-52).
+ * gfk_thin_batched runs gfk_thin's single-launch greedy search for n_chains problems in ONE cooperative launch: the grid
+ * is split into one group of CTAs per chain, every group with its own workspace and exchange slots, so a set of
+ * small chains pays the per-step latency floor once instead of n_chains times.  Single rank (chains are dealt over
+ * ranks by the caller, no data-path collective).
+ *   problems   : HOST array of n_chains structs (device pointers inside), all with the same d <= 4, mode and kernel kind
+ *                (lw / w both present or both absent) and a scalar preconditioner
+ *   objectives : HOST array of n_chains device pointers, problems[c].n doubles each (out)
+ *   idx_outs   : HOST array of n_chains device pointers, m uint32 each (out)
+ *   ws         : device scratch of gfk_thin_batched_ws_bytes(n_chains) bytes, 256-byte aligned
+ * Returns GFK_EUNSUPPORTED (nothing launched) when the set is not eligible - d > 4, mixed kinds, a chain too long for
+ * the shared memory of its CTA group, more chains than SMs: the caller then loops over gfk_thin.  Asynchronous;
+ * gfk_thin_batched_check is the synchronous counterpart of gfk_thin_check for the whole set. */
+size_t gfk_thin_batched_ws_bytes(int32_t n_chains);
+int gfk_thin_batched(const gfk_problem* problems, int32_t n_chains, int32_t m, double* const* objectives,
+                     uint32_t* const* idx_outs, void* ws, void* stream);
+int gfk_thin_batched_check(const void* ws, int32_t n_chains, void* stream);
+
 /* ---- a7: stein_thinning.stein.ksd / kmat ----------------------------------------------
  * gfk_ksd_rowsums: for the rows sel[0..m) of the replica (sel == NULL: rows 0..m-1),
  *   low[t] = sum_{b<t} k(sel[t], sel[b]),  diag[t] = k(sel[t], sel[t]).

@@ -248,6 +248,26 @@ class SimProblem:
         return out.copy()
 
 
+def thin_batched(problems, m):
+    """gfk_thin_batched over SimProblems: index vectors and objectives per chain, or None when the set is not eligible."""
+    lib = load()
+    n = len(problems)
+    structs = (Problem * n)(*[p.struct for p in problems])
+    objectives = [guarded((p.n,), np.float64, fill=np.nan) for p in problems]
+    idx = [guarded((m,), np.uint32, fill=0xffffffff) for _ in problems]
+    obj_ptrs = (ctypes.c_void_p * n)(*[o.ctypes.data for o in objectives])
+    idx_ptrs = (ctypes.c_void_p * n)(*[i.ctypes.data for i in idx])
+    nbytes = lib.gfk_thin_batched_ws_bytes(n)
+    raw = guarded((nbytes + 256,), np.uint8, fill=0xa5)
+    base = (raw.ctypes.data + 255) // 256 * 256
+    rc = lib.gfk_thin_batched(structs, n, m, obj_ptrs, idx_ptrs, ctypes.c_void_p(base), None)
+    if rc == 4:                                          # GFK_EUNSUPPORTED
+        return None
+    check(rc)
+    check(lib.gfk_thin_batched_check(ctypes.c_void_p(base), n, None))
+    return [i.copy() for i in idx], [o.copy() for o in objectives]
+
+
 # ---- SURVEY 8f rows: proxies and energy distance through the emulated kernels -----------------------------------
 def student_t_proxy(x, mu, sigma, df):
     from math import lgamma

@@ -653,6 +653,50 @@ def test_tma_fed_step_kernel_equals_the_slab_kernel(d, monkeypatch):
     assert lib.simt_tma_loads() == before
 
 
+@pytest.mark.parametrize('sms', [3, 7, 12])
+def test_batched_chains_in_one_launch_equal_one_job_per_chain(sms, monkeypatch):
+    """gfk_thin_batched: several chains of different lengths in ONE cooperative launch,
+    one group of CTAs per chain with its own workspace and slots, must return exactly what one gfk_thin per chain
+    returns - index vectors and running objectives bit for bit, i.e. the oracle's sequences - for the score-based and
+    the gradient-free kernel, in every precision, under random thread schedules."""
+    monkeypatch.setenv('SIMT_SMS', str(sms))
+    rng = np.random.default_rng(4200 + sms)
+    m = 25
+    for d, gf in ((4, True), (2, False), (3, True)):
+        chains = []
+        for n in (700, 1500, 2300):
+            x, g = _mcmc_like(rng, n, d)
+            log_p = -0.5 * np.sum(x ** 2, axis=1)
+            chains.append((x, g, log_p, log_p + 0.5 * np.sin(x[:, 0])))
+        for precision in ('f64', 'f64-fast', 'f32'):
+            mk = (lambda c: H.SimProblem(c[0], c[1], c[2], c[3], preconditioner='med', precision=precision)) if gf else \
+                 (lambda c: H.SimProblem(c[0], c[1], preconditioner='med', precision=precision))
+            probs = [mk(c) for c in chains]
+            single = [p.thin(m) for p in probs]
+            for random, seed in ((False, 0), (True, 3)):
+                H.set_schedule(random, seed)
+                got = H.thin_batched(probs, m)
+                assert got is not None, 'an eligible set was refused'
+                for c in range(len(chains)):
+                    assert np.array_equal(got[0][c], single[c][0]), (d, gf, precision, c, random)
+                    assert np.array_equal(got[1][c], single[c][1]), (d, gf, precision, c, random)
+            H.set_schedule(False)
+            if precision == 'f64':
+                for c, ch in enumerate(chains):
+                    want = ot.thin_gf(ch[0], ch[2], ch[3], ch[1], m, preconditioner='med') if gf else \
+                        ot.thin(ch[0], ch[1], m, preconditioner='med')
+                    assert np.array_equal(single[c][0], want), (d, gf, c)
+    # not eligible -> refused without launching anything: d > 4, mixed kernel kinds, more chains than SMs
+    x5, g5 = _mcmc_like(rng, 400, 5)
+    assert H.thin_batched([H.SimProblem(x5, g5), H.SimProblem(x5, g5)], 5) is None
+    x4, g4 = _mcmc_like(rng, 400, 4)
+    lp = -0.5 * np.sum(x4 ** 2, axis=1)
+    assert H.thin_batched([H.SimProblem(x4, g4), H.SimProblem(x4, g4, lp, lp + 0.1 * x4[:, 0])], 5) is None
+    assert H.thin_batched([H.SimProblem(x4, g4) for _ in range(sms + 1)], 5) is None
+    one = H.thin_batched([H.SimProblem(x4, g4)], 5)                      # a set of one is just a job
+    assert np.array_equal(one[0][0], ot.thin(x4, g4, 5))
+
+
 def test_full_size_c3_on_the_b200_grid_shape(monkeypatch):
     """BASELINE config C3 at full size (n = 10^6, d = 4, gradient-free, 'med') with the launch geometry of a B200:
     148 concurrently running CTAs of 512 threads, 14 rows per thread of which 3 stay in shared memory, every CTA

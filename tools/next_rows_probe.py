@@ -76,5 +76,19 @@ x = torch.from_numpy(rng.standard_normal((1_000_000, 4))).cuda()
 cov = np.eye(4) + 0.1
 t = timed(lambda: proxies._t_proxy_device(x, np.zeros(4), cov, 9.0))
 note('student_t:1e6:4', seconds=t, gb_per_s=1_000_000 * (32 + 8 + 32) / t / 1e9)
+# five chains per call (lotka_volterra/Stein_thinning.ipynb#c17): one batched cooperative launch vs one job per chain
+from gradient_free_mcmc_postprocessing_b200._engine import thin_batched  # noqa: E402
+for n_chain, m_chain in ((40_000, 1000), (200_000, 1000), (500_000, 1000)):
+    cs = [synthetic.config_c2(n=n_chain, m=m_chain, seed=12345 + i) for i in range(5)]
+    probs = [SteinProblem(torch.from_numpy(c['sample']).cuda(), torch.from_numpy(c['gradient']).cuda(), preconditioner='med')
+             for c in cs]
+    seq = timed(lambda: [p.thin(m_chain) for p in probs], reps=2)
+    bat_idx = thin_batched(probs, m_chain)
+    if bat_idx is None:
+        note(f'chains5:{n_chain}', sequential_s=seq, batched='not eligible')
+        continue
+    same = all(np.array_equal(a, p.thin(m_chain)) for a, p in zip(bat_idx, probs))
+    bat = timed(lambda: thin_batched(probs, m_chain), reps=2)
+    note(f'chains5:{n_chain}', sequential_s=seq, batched_s=bat, speedup=seq / bat, same_indices=bool(same))
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'next_rows_probe.json'), 'w'), indent=1)
