@@ -30,6 +30,26 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         }                                 \
     } while (0)
 
+// dynamic shared memory of the running block as `unsigned char* name` (headers are not run through the test suite's
+// launch-syntax rewriter, so kernels that live in a .cuh declare it through this)
+#if defined(GFK_SIMT_HOST)
+#define GFK_DYN_SMEM(name) unsigned char* name = reinterpret_cast<unsigned char*>(simt::dyn_smem())
+#else
+#define GFK_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+// nanosecond wall clock of the device (%globaltimer); every bounded wait of the library measures against it
+__device__ __forceinline__ unsigned long long gfk_timer_ns() {
+#if defined(GFK_SIMT_HOST)
+    return simt::now_ns();
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+    return t;
+#endif
+}
+
+
 int sm_count();
 // running count of kernel launches issued by this library (gfk_launch_count)
 void count_launches(long long n);

@@ -420,6 +420,10 @@ static int rowsums_typed(const gfk_problem* p, const uint32_t* sel, int64_t m, i
     return GFK_OK;
 }
 
+}  // namespace gfk
+#include "ksd_mma.cuh"
+namespace gfk {
+
 static int check_problem(const gfk_problem* p, const char* who) {
     GFK_REQUIRE(p && p->x && p->s, "%s: NULL problem / x / s", who);
     GFK_REQUIRE(p->n >= 1 && p->d >= 1, "%s: empty problem", who);
@@ -444,6 +448,95 @@ extern "C" int gfk_ksd_rowsums(const gfk_problem* p, const uint32_t* sel, int64_
     // FMA formulation here (KSD values are checked to 1e-10 relative, not bit for bit)
     if (p->mode == GFK_F32_FAST) return rowsums_typed<float>(p, sel, m, part, n_parts, low, diag, st);
     return rowsums_typed<double>(p, sel, m, part, n_parts, low, diag, st);
+}
+
+// ---- tensor-core row sums (ksd_mma.cuh): float32 mode, scalar preconditioner, 32 <= d <= 64 ----------------------
+static inline long long mma_pad_rows(long long m) { return (m + MM_M - 1) / MM_M * MM_M; }
+static inline int mma_pad_dims(int d) { return (d + MM_KB - 1) / MM_KB * MM_KB; }
+
+extern "C" int gfk_ksd_mma_supported(const gfk_problem* p) {
+    return (p && p->mode == GFK_F32_FAST && !p->xl && p->d >= 32 && p->d <= 64) ? 1 : 0;
+}
+
+extern "C" size_t gfk_ksd_mma_ws_bytes(int64_t m, int32_t d) {
+    if (m < 1 || d < 1) return 0;
+    const size_t mp = (size_t)mma_pad_rows(m), dp = (size_t)mma_pad_dims(d);
+    return 512 + sizeof(double) * dp + 4 * sizeof(float) * mp * dp + 3 * sizeof(float) * mp + 1024;
+}
+
+extern "C" int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, int64_t m, double* low, double* diag,
+                                   void* ws, void* stream) {
+    int rc = check_problem(p, "gfk_ksd_rowsums_mma");
+    if (rc) return rc;
+    GFK_REQUIRE(low && diag && ws && m >= 1, "gfk_ksd_rowsums_mma: bad arguments");
+    GFK_REQUIRE(sel || m <= p->n, "gfk_ksd_rowsums_mma: m = %lld exceeds n = %lld", (long long)m, (long long)p->n);
+    GFK_REQUIRE(m < 0x7fffff00LL, "gfk_ksd_rowsums_mma: m too large for 32-bit tensor-map coordinates");
+    if (!gfk_ksd_mma_supported(p)) {
+        set_error("gfk_ksd_rowsums_mma: needs the float32 mode, a scalar preconditioner and 32 <= d <= 64");
+        return GFK_EUNSUPPORTED;
+    }
+    GFK_REQUIRE(reinterpret_cast<uintptr_t>(ws) % 256 == 0, "gfk_ksd_rowsums_mma: ws must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int d = p->d, dp = mma_pad_dims(d), nkb = dp / MM_KB;
+    const long long mp = mma_pad_rows(m);
+    char* w8 = static_cast<char*>(ws);
+    unsigned* status = reinterpret_cast<unsigned*>(w8);                 // first 256 bytes: the status word
+    double* mean = reinterpret_cast<double*>(w8 + 256);
+    float* xh = reinterpret_cast<float*>(w8 + 512 + sizeof(double) * dp);
+    xh = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(xh) + 255) & ~(uintptr_t)255);
+    float* xl = xh + (size_t)mp * dp;
+    float* sh = xl + (size_t)mp * dp;
+    float* sl = sh + (size_t)mp * dp;
+    float* nx = sl + (size_t)mp * dp;
+    float* sxx = nx + mp;
+    float* wout = sxx + mp;
+    const float* x = static_cast<const float*>(p->x);
+    const float* s = static_cast<const float*>(p->s);
+    // the diagonal (and the zeroing convention of the row sums) is the tile kernel's
+    KsdArgs<float> a = make_args<float>(p, sel, m);
+    a.low = low;
+    a.diag = diag;
+    GFK_CUDA(cudaMemsetAsync(status, 0, 256, st));
+    ksd_diag_kernel<float><<<grid1d(m), 256, 0, st>>>(a);
+    ksd_mma_colmean_kernel<><<<d, 256, 0, st>>>(x, sel, m, d, mean);
+    ksd_mma_split_kernel<><<<grid1d(mp * 32), 256, 0, st>>>(x, s, static_cast<const float*>(p->lw), static_cast<const float*>(p->w),
+                                                           sel, m, mp, d, dp, mean, xh, xl, sh, sl, nx, sxx, wout);
+    TensorMap maps[4];
+    float* arrays[4] = {xh, xl, sh, sl};
+    for (int i = 0; i < 4; ++i) {
+        if (!make_tensor_map_2d(&maps[i], arrays[i], 4, (unsigned long long)dp, (unsigned long long)mp, MM_KB, MM_N)) {
+            set_error("gfk_ksd_rowsums_mma: cuTensorMapEncodeTiled is unavailable or refused the layout");
+            return GFK_EUNSUPPORTED;
+        }
+    }
+    KsdMmaArgs ma;
+    ma.nx = nx;
+    ma.sxx = sxx;
+    ma.w = p->lw ? wout : nullptr;
+    ma.m = m;
+    ma.nkb = nkb;
+    ma.kp = a.kp;
+    ma.low = low;
+    ma.status = status;
+    const size_t smem = ksd_mma_smem_bytes(nkb);
+    GFK_CUDA(cudaFuncSetAttribute(ksd_mma_kernel<>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ksd_mma_kernel<><<<(unsigned)(mp / MM_M), MM_THREADS, smem, st>>>(ma, maps[0], maps[1], maps[2], maps[3]);
+    count_launches(4);
+    GFK_CHECK_LAUNCH();
+    return GFK_OK;
+}
+
+extern "C" int gfk_ksd_mma_check(const void* ws, void* stream) {
+    GFK_REQUIRE(ws, "gfk_ksd_mma_check: NULL workspace");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned flag = 0;
+    GFK_CUDA(cudaMemcpyAsync(&flag, ws, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    GFK_CUDA(cudaStreamSynchronize(st));
+    if (flag) {
+        set_error("gfk_ksd_rowsums_mma: a pipeline wait inside the kernel ran past its deadline; the row sums are invalid");
+        return GFK_ECUDA;
+    }
+    return GFK_OK;
 }
 
 extern "C" int gfk_ksd_finish(const double* low, const double* diag, int64_t m, double* ks, void* stream) {

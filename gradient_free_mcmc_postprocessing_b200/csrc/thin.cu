@@ -18,11 +18,8 @@
 #include <type_traits>
 #include <vector>
 
-#if !defined(GFK_SIMT_HOST)
-#include <cuda.h>      // CUtensorMap and its enums only: cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint
-#endif
-
 #include "common.cuh"
+#include "tma.cuh"
 #include "comm.h"
 
 namespace gfk {
@@ -157,16 +154,6 @@ constexpr unsigned kSpinCheckEvery = 64u;  // read the timer every 64th unsucces
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     return *reinterpret_cast<const volatile unsigned*>(p);
-}
-
-__device__ __forceinline__ unsigned long long gfk_timer_ns() {
-#if defined(GFK_SIMT_HOST)
-    return simt::now_ns();
-#else
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
-    return t;
-#endif
 }
 
 // one per wait loop; expired() is called after every unsuccessful polling round
@@ -746,52 +733,6 @@ __global__ void __launch_bounds__(kThreads) thin_step_chunked_kernel(ThinArgs<T>
 // row state lives in ChunkRow, the slab loop is flattened over (tile, slab) stages.  Rows past the end of the sample
 // and dimensions past d are zero-filled by the copy engine and never read.
 // [round 2: opt-in with GFK_STEP_TMA=1; executed on the CPU emulator of the test suite only, not yet on a GPU]
-#if defined(GFK_SIMT_HOST)
-using TensorMap = simt::TensorMap2D;
-__device__ __forceinline__ void dev_mbar_init(unsigned long long* bar, int count) { simt::mbar_init(bar, count); }
-__device__ __forceinline__ void dev_mbar_fence_init() { }
-__device__ __forceinline__ void dev_mbar_arrive(unsigned long long* bar) { simt::mbar_arrive(bar); }
-__device__ __forceinline__ void dev_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) { simt::mbar_arrive_expect_tx(bar, bytes); }
-__device__ __forceinline__ void dev_mbar_wait(unsigned long long* bar, unsigned parity) {
-    while (!simt::mbar_test(bar, parity)) simt::poll_yield();
-}
-__device__ __forceinline__ void dev_tma_load_2d(void* dst, const TensorMap* map, int c0, int c1, unsigned long long* bar) {
-    simt::tma_load_2d(dst, map, c0, c1, bar);
-}
-#else
-using TensorMap = CUtensorMap;
-__device__ __forceinline__ void dev_mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-// makes the initialised barriers visible to the async proxy (the copy engine) before the first copy names them
-__device__ __forceinline__ void dev_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void dev_mbar_arrive(unsigned long long* bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}"
-                 ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void dev_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
-                 ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void dev_mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "GFK_MBAR_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra GFK_MBAR_DONE;\n\t"
-        "bra GFK_MBAR_WAIT;\n\t"
-        "GFK_MBAR_DONE:\n\t"
-        "}" ::"r"(addr), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void dev_tma_load_2d(void* dst, const TensorMap* map, int c0, int c1, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(reinterpret_cast<unsigned long long>(map)),
-                   "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1) : "memory");
-}
-#endif
-
 constexpr int kTmaRows = 256;                        // rows of a tile = consumer threads
 constexpr int kTmaStages = 3;
 constexpr int kTmaThreads = kTmaRows + 32;           // + the producer warp
@@ -938,7 +879,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) thin_step_tma_kernel(ThinArgs<
             for (long long q = 0; q < nstages; ++q) {
                 const int st = (int)(q % kTmaStages);
                 const long long use = q / kTmaStages;                       // how often this buffer was filled before
-                if (use > 0) dev_mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1));   // its previous contents are consumed
+                if (use > 0) dev_mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1), &a.ws->abort);   // its previous contents are consumed
                 const long long it = q / nslabs;
                 const int k0 = (int)(q - it * nslabs) * KS;
                 const long long row0 = a.row_begin + first + it * stride;       // global row of the tile's first row
@@ -956,7 +897,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) thin_step_tma_kernel(ThinArgs<
         const unsigned r7 = threadIdx.x & 7u;
         for (long long q = 0; q < nstages; ++q) {
             const int st = (int)(q % kTmaStages);
-            dev_mbar_wait(&full_bar[st], (unsigned)((q / kTmaStages) & 1));          // both tiles of slab q have landed
+            dev_mbar_wait(&full_bar[st], (unsigned)((q / kTmaStages) & 1), &a.ws->abort);   // both tiles of slab q have landed
             const long long it = q / nslabs;
             const int slab = (int)(q - it * nslabs);
             const int k0 = slab * KS;
@@ -1550,47 +1491,11 @@ static size_t step_tma_smem(int d) {
     return 1024 + (size_t)kTmaStages * 2 * kTmaTileBytes + sizeof(T) * 2 * (size_t)d;
 }
 
-// 2-D tensor map over a row-major (n, d) array: box = [128 bytes of dims] x [kTmaRows rows], SWIZZLE_128B,
-// out-of-bounds elements read as zero.  false: the driver entry point is missing or refused the layout.
+// tensor map of one array for the TMA-fed step kernel: box = [128 bytes of dims] x [kTmaRows rows]
 template <typename T>
 static bool make_step_tensor_map(TensorMap* map, const T* base, long long n, int d) {
-#if defined(GFK_SIMT_HOST)
-    memset(map, 0, sizeof(*map));
-    map->magic = 0x7a3du;
-    map->elem = (unsigned)sizeof(T);
-    map->box0 = (unsigned)TmaSlab<T>::K;
-    map->box1 = (unsigned)kTmaRows;
-    map->swizzle = 128;
-    map->base = base;
-    map->dim0 = (unsigned long long)d;
-    map->dim1 = (unsigned long long)n;
-    map->stride1 = (unsigned long long)d * sizeof(T);
-    return true;
-#else
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    static bool looked = false;
-    if (!looked) {
-        looked = true;
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            encode = reinterpret_cast<EncodeFn>(fn);
-        else
-            cudaGetLastError();
-    }
-    if (!encode) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
-    const cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(T)};
-    const cuuint32_t box[2] = {(cuuint32_t)TmaSlab<T>::K, (cuuint32_t)kTmaRows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    return encode(map, dt, 2, const_cast<T*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-#endif
+    return make_tensor_map_2d(map, base, (unsigned)sizeof(T), (unsigned long long)d, (unsigned long long)n,
+                              (unsigned)TmaSlab<T>::K, (unsigned)kTmaRows);
 }
 
 template <typename T, bool STRICT>

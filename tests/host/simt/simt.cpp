@@ -90,6 +90,7 @@ struct Block {
     void* sched_sp = nullptr;
     Fiber* running = nullptr;
     char* smem = nullptr;
+    char* smem_window = nullptr;        // what shared-window addresses (descriptors) are relative to
     const std::function<void()>* fn = nullptr;
     bool failed = false;
     unsigned polls = 0;
@@ -313,6 +314,78 @@ void cp_async_wait(int allow_pending_groups) {
 }
 
 static std::atomic<long long> g_tma_loads{0};
+static std::atomic<long long> g_umma_issued{0};
+
+// shared-window address of a pointer into dynamic shared memory (what cvta.to.shared gives on the device)
+unsigned smem_u32(const void* p) {
+    Block* b = t_blk;
+    const char* c = static_cast<const char*>(p);
+    if (!b->smem_window || c < b->smem || c >= b->smem_window + 256 * 1024) fail("shared-window address of a pointer outside dynamic shared memory");
+    return (unsigned)(c - b->smem_window);
+}
+
+// ---- tcgen05.mma.cta_group::1.kind::tf32, both operands from shared memory, K-major, SWIZZLE_128B ---------------
+// D[lane r][column c0 + j] (+)= sum_k A[r][k] * B[j][k],  r < M, j < N, k < 8 (one instruction = 32 bytes of K).
+// The shared-memory descriptors are decoded as cute::UMMA::SmemDescriptor lays them out: start address and stride
+// byte offset in 16-byte units, version 1, layout type 2 = SWIZZLE_128B; an element's address is
+// start + (row / 8) * SBO + (row % 8) * 128 + 4 k with address bits [4,7) XOR-ed by bits [7,10).  Operands are
+// read as tf32 (the low 13 mantissa bits do not take part); products are accumulated in float in k order.
+static float tf32_of(unsigned bits) {
+    bits &= 0xffffe000u;
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+void umma_tf32(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b, unsigned idesc, bool accumulate) {
+    Block* b = t_blk;
+    g_umma_issued.fetch_add(1, std::memory_order_relaxed);
+    if (!b->tmem_cols) fail("tcgen05.mma without a tensor-memory allocation");
+    const unsigned c_format = (idesc >> 4) & 3u, a_format = (idesc >> 7) & 7u, b_format = (idesc >> 10) & 7u;
+    const unsigned a_major = (idesc >> 15) & 1u, b_major = (idesc >> 16) & 1u;
+    const unsigned N = ((idesc >> 17) & 0x3fu) << 3, M = ((idesc >> 24) & 0x1fu) << 4;
+    if (c_format != 1 || a_format != 2 || b_format != 2) fail("tcgen05.mma kind::tf32: instruction descriptor formats %u/%u/%u", c_format, a_format, b_format);
+    if (a_major != 0 || b_major != 0) fail("tcgen05.mma: the emulator models K-major operands only");
+    if (M != 128 || N < 8 || N > 256 || N % 8) fail("tcgen05.mma: shape M = %u, N = %u", M, N);
+    if ((idesc & 0xfu) || (idesc >> 30)) fail("tcgen05.mma: sparse / saturate / shift bits set in the instruction descriptor");
+    const unsigned lane0 = tmem_d >> 16, col0 = tmem_d & 0xffffu;
+    if (lane0 != 0 || col0 + N > (unsigned)b->tmem_cols) fail("tcgen05.mma: accumulator columns %u..%u beyond the allocation", col0, col0 + N);
+    auto operand = [&](unsigned long long desc, unsigned rows, const char* which, std::vector<float>& out) {
+        const unsigned start = (unsigned)(desc & 0x3fffu) << 4, sbo = (unsigned)((desc >> 32) & 0x3fffu) << 4;
+        const unsigned version = (unsigned)((desc >> 46) & 3u), layout = (unsigned)((desc >> 61) & 7u);
+        const unsigned base_offset = (unsigned)((desc >> 49) & 7u);
+        if (version != 1) fail("tcgen05.mma: %s descriptor version %u (Blackwell: 1)", which, version);
+        if (layout != 2) fail("tcgen05.mma: %s descriptor layout type %u (the emulator models SWIZZLE_128B = 2)", which, layout);
+        if (base_offset != 0) fail("tcgen05.mma: %s descriptor base offset %u", which, base_offset);
+        if (sbo != 1024) fail("tcgen05.mma: %s descriptor stride byte offset %u (8 rows of 128 bytes = 1024)", which, sbo);
+        if ((start & 0x7fu) % 32 != 0 || (start & 0x7fu) + 32 > 128) fail("tcgen05.mma: %s K offset inside the swizzle atom", which);
+        if (((start & ~0x7fu) % 1024) != 0) fail("tcgen05.mma: %s tile is not 1024-byte aligned (SWIZZLE_128B)", which);
+        out.resize((size_t)rows * 8);
+        for (unsigned r = 0; r < rows; ++r)
+            for (unsigned k = 0; k < 8; ++k) {
+                unsigned addr = start + (r / 8) * sbo + (r % 8) * 128 + 4 * k;
+                addr ^= ((addr >> 7) & 7u) << 4;
+                const char* p = b->smem_window + addr;
+                if (p < b->smem) fail("tcgen05.mma: %s operand outside dynamic shared memory", which);
+                unsigned bits;
+                memcpy(&bits, p, 4);
+                out[(size_t)r * 8 + k] = tf32_of(bits);
+            }
+    };
+    std::vector<float> A, B;
+    operand(desc_a, M, "A", A);
+    operand(desc_b, N, "B", B);
+    for (unsigned r = 0; r < M; ++r)
+        for (unsigned j = 0; j < N; ++j) {
+            unsigned* cell = b->tmem.data() + (size_t)r * 512 + col0 + j;
+            float acc = 0.f;
+            if (accumulate) memcpy(&acc, cell, 4);
+            for (unsigned k = 0; k < 8; ++k) acc = fmaf(A[(size_t)r * 8 + k], B[(size_t)j * 8 + k], acc);
+            memcpy(cell, &acc, 4);
+        }
+}
+// tcgen05.commit.mbarrier::arrive::one: the MMAs issued so far have completed (the emulator runs them at issue)
+void umma_commit(unsigned long long* bar) { mbar_arrive(bar); }
+
 // ---- mbarrier: [63] phase, [62:48] pending arrivals, [47:32] arrival count of a phase, [31:0] pending bytes (signed) ----
 namespace {
 struct Mbar {
@@ -411,7 +484,8 @@ void tma_load_2d(void* dst, const TensorMap2D* map, int c0, int c1, unsigned lon
 }
 
 }  // namespace simt
-extern "C" long long simt_tma_loads() { return simt::g_tma_loads.load(); }   // tests: did the TMA kernel run at all?
+extern "C" long long simt_tma_loads() { return simt::g_tma_loads.load(); }
+extern "C" long long simt_umma_issued() { return simt::g_umma_issued.load(); }   // tests: did the TMA kernel run at all?
 namespace simt {
 unsigned long long now_ns() {
     struct timespec ts;
@@ -602,7 +676,10 @@ void launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::fun
         b.fibers.resize((size_t)T);
         b.fn = &fn;
         char* stacks = stacks_acquire(stack_bytes);
-        b.smem = smem ? static_cast<char*>(aligned_alloc(128, (smem + 127) / 128 * 128)) : nullptr;
+        // the shared-memory window starts on a 1024-byte boundary; dynamic shared memory sits 128 bytes into it, as it
+        // would behind some static shared memory: only 128-byte aligned, so kernels must align swizzled tiles themselves
+        b.smem_window = smem ? static_cast<char*>(aligned_alloc(1024, (smem + 128 + 1023) / 1024 * 1024)) : nullptr;
+        b.smem = smem ? b.smem_window + 128 : nullptr;
         t_blk = &b;
         if (one_block_only) {
             run_block(b, stacks, (unsigned)fixed_block, grid, block, smem);
@@ -614,7 +691,7 @@ void launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::fun
             }
         }
         t_blk = nullptr;
-        free(b.smem);
+        free(b.smem_window);
         stacks_release(stack_bytes, stacks);
     };
     if (cooperative) {

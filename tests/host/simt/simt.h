@@ -96,6 +96,11 @@ void mbar_arrive(unsigned long long* bar);
 void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes);
 bool mbar_test(unsigned long long* bar, unsigned parity);
 void tma_load_2d(void* dst, const TensorMap2D* map, int c0, int c1, unsigned long long* bar);
+// shared-window address (cvta.to.shared) of a pointer into dynamic shared memory; tcgen05.mma kind::tf32 with both
+// operands K-major SWIZZLE_128B in shared memory and the accumulator in tensor memory; tcgen05.commit
+unsigned smem_u32(const void* p);
+void umma_tf32(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b, unsigned idesc, bool accumulate);
+void umma_commit(unsigned long long* bar);
 
 // grid x block fibers run fn(); cooperative: all blocks concurrently
 void launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& fn);

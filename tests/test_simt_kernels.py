@@ -697,6 +697,50 @@ def test_batched_chains_in_one_launch_equal_one_job_per_chain(sms, monkeypatch):
     assert np.array_equal(one[0][0], ot.thin(x4, g4, 5))
 
 
+@pytest.mark.parametrize('d', [32, 40, 64])
+def test_tensor_core_ksd_row_sums(d):
+    """gfk_ksd_rowsums_mma (csrc/ksd_mma.cuh): the four Gram tiles of the KSD on tcgen05.mma kind::tf32 with 3xTF32
+    operand splits, operands by TMA into SWIZZLE_128B tiles, accumulators in tensor memory, the tile kernel's pair
+    epilogue on top.  The emulator decodes the shared-memory and instruction descriptors the kernel builds (bit layouts
+    of cute::UMMA), keeps 11 significant bits of every operand and accumulates in float.  float32 mode: KSD values
+    within 1e-5 relative of the float64 oracle (BASELINE.json), row sums close to the SIMT float32 kernel's, identical
+    under random thread schedules; a selection with repeats; ineligible problems refused."""
+    rng = np.random.default_rng(7700 + d)
+    n = 330                                                  # 3 row tiles of 128, 6 column tiles of 64
+    x, g = _mcmc_like(rng, n, d, dup=0.1)
+    x = x + 3.0                                              # an offset the centring has to remove
+    g = g / np.sqrt(d)
+    log_p = -0.5 * np.sum((x - 3.0) ** 2, axis=1) / d
+    log_q = log_p + 0.3 * np.sin(x[:, 0])
+    lib = H.load()
+    lib.simt_umma_issued.restype = ctypes.c_longlong
+    for gf in (False, True):
+        p = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision='f32') if gf else \
+            H.SimProblem(x, g, preconditioner='med', precision='f32')
+        ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med') if gf else \
+            ot._make_stein_integrand(x, g, preconditioner='med')
+        H.set_schedule(False)
+        before = lib.simt_umma_issued()
+        low, diag = p.ksd_rowsums_mma()
+        assert lib.simt_umma_issued() > before
+        simt_low, simt_diag = p.ksd_rowsums()
+        assert np.array_equal(diag, simt_diag)
+        scale = np.maximum(np.abs(simt_low), np.max(np.abs(simt_low)) * 1e-3)
+        assert np.max(np.abs(low - simt_low) / scale) < 2e-4, np.max(np.abs(low - simt_low) / scale)
+        np.testing.assert_allclose(p.ksd_from_rowsums(low, diag), os_.ksd(ref, n), rtol=1e-5)
+        H.set_schedule(True, 4)
+        low2, _ = p.ksd_rowsums_mma()
+        assert np.array_equal(low2, low), gf
+        H.set_schedule(False)
+        sel = rng.integers(0, n, 200)
+        lo_s, dg_s = p.ksd_rowsums_mma(sel=sel)
+        np.testing.assert_allclose(p.ksd_from_rowsums(lo_s, dg_s), os_.ksd(lambda i, j: ref(sel[i], sel[j]), 200), rtol=1e-5)
+    # not eligible: float64 modes, d outside [32, 64]
+    assert H.SimProblem(x, g, preconditioner='med', precision='f64-fast').ksd_rowsums_mma() is None
+    xs, gs = _mcmc_like(rng, 100, 16)
+    assert H.SimProblem(xs, gs, preconditioner='med', precision='f32').ksd_rowsums_mma() is None
+
+
 def test_full_size_c3_on_the_b200_grid_shape(monkeypatch):
     """BASELINE config C3 at full size (n = 10^6, d = 4, gradient-free, 'med') with the launch geometry of a B200:
     148 concurrently running CTAs of 512 threads, 14 rows per thread of which 3 stay in shared memory, every CTA

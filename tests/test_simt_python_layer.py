@@ -133,6 +133,30 @@ def test_ksd_and_kmat_through_the_public_api(api, gf):
     np.testing.assert_allclose(ks, os_.ksd(repo_glue.reindex_integrand(ref, sel), 111), rtol=1e-10)
 
 
+def test_tensor_core_ksd_through_the_public_api(api, monkeypatch):
+    """GFK_KSD_MMA=1 routes ksd() of a float32, 32 <= d <= 64 problem through gfk_ksd_rowsums_mma; anything else keeps
+    the tile kernel.  Values within the float32 bar (1e-5 relative) of the float64 oracle."""
+    rng = np.random.default_rng(61)
+    x, g = _mcmc_like(rng, 300, 48, dup=0.1)
+    g = g / 7.0
+    ref = ot._make_stein_integrand(x, g, preconditioner='med')
+    want = os_.ksd(ref, 300)
+    lib = H.load()
+    lib.simt_umma_issued.restype = ctypes.c_longlong
+    monkeypatch.setenv('GFK_KSD_MMA', '1')
+    integ = api.thinning._make_stein_integrand(x, g, preconditioner='med', precision='f32')
+    before = lib.simt_umma_issued()
+    np.testing.assert_allclose(api.stein.ksd(integ, 300), want, rtol=1e-5)
+    assert lib.simt_umma_issued() > before
+    before = lib.simt_umma_issued()
+    integ64 = api.thinning._make_stein_integrand(x, g, preconditioner='med', precision='f64')
+    np.testing.assert_allclose(api.stein.ksd(integ64, 300), want, rtol=1e-10)
+    assert lib.simt_umma_issued() == before                     # float64: the tile kernel
+    monkeypatch.delenv('GFK_KSD_MMA')
+    np.testing.assert_allclose(api.stein.ksd(integ, 300), want, rtol=1e-5)
+    assert lib.simt_umma_issued() == before                     # not opted in: the tile kernel
+
+
 def test_validation_errors_through_the_public_api(api):
     rng = np.random.default_rng(12)
     x, g = rng.standard_normal((50, 2)), rng.standard_normal((50, 2))

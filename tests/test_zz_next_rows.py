@@ -4,6 +4,7 @@ closed for the round: the kernels under them have been executed by the CPU emula
 xfail until a GPU run has confirmed them: a pass shows up as XPASS, a failure does not mask the verified suite.  The
 file sorts last on purpose (the driver runs pytest with -x).
 """
+import os
 import warnings
 
 import numpy as np
@@ -115,3 +116,31 @@ def test_chain_batched_thinning_and_npy_layer(gpu_device, g13, tmp_path):
         assert np.array_equal(np.load(outs[i]), oracle_thin(g13['sample'][i * 100:], g13['gradient'][i * 100:], 20))
     mine = thin_chains([p[0] for p in paths], [p[1] for p in paths], 20, rank=1, world=2, device=gpu_device)
     assert mine[0] is None and mine[2] is None and np.array_equal(mine[1], res[1])
+
+
+@pytest.mark.skipif(os.environ.get('GFK_TEST_OPTIN_KERNELS') != '1',
+                    reason='opt-in kernels that have never run on a GPU: first contact goes through '
+                           'tools/r02_contact_1gpu.sh (compute-sanitizer first), not through the plain suite')
+def test_tensor_core_and_tma_variants_on_device(gpu_device, monkeypatch):
+    """The two opt-in Blackwell-specific kernels of round 2, written without GPU access (emulator-verified):
+    GFK_KSD_MMA=1 - KSD row sums on tcgen05.mma kind::tf32 (csrc/ksd_mma.cuh), float32 bar 1e-5 against the oracle;
+    GFK_STEP_TMA=1 - the d > 4 greedy step fed by cp.async.bulk.tensor (csrc/thin.cu), index-exact against the oracle
+    and bit-identical in the objective to the default kernel."""
+    from gradient_free_mcmc_postprocessing_b200.stein import ksd
+    from gradient_free_mcmc_postprocessing_b200.thinning import _make_stein_integrand, thin
+    from gradient_free_mcmc_postprocessing_b200._engine import SteinProblem
+    from oracle.stein_thinning_oracle import stein as os_, thinning as ot
+    rng = np.random.default_rng(77)
+    n, d = 3000, 64
+    x = rng.standard_normal((n, d)) + 2.0
+    g = -(x - 2.0) * (1 + 0.05 * np.arange(d)) / np.sqrt(d)
+    want = os_.ksd(ot._make_stein_integrand(x, g, preconditioner='med'), n)
+    monkeypatch.setenv('GFK_KSD_MMA', '1')
+    got = ksd(_make_stein_integrand(x, g, preconditioner='med', precision='f32', device=gpu_device), n)
+    np.testing.assert_allclose(got, want, rtol=1e-5)
+    monkeypatch.delenv('GFK_KSD_MMA')
+    base_idx, base_obj = SteinProblem(x, g, preconditioner='med', device=gpu_device).thin(60, return_objective=True)
+    monkeypatch.setenv('GFK_STEP_TMA', '1')
+    idx, obj = SteinProblem(x, g, preconditioner='med', device=gpu_device).thin(60, return_objective=True)
+    assert np.array_equal(idx, base_idx) and bool((obj == base_obj).all())
+    assert np.array_equal(idx, ot.thin(x, g, 60, preconditioner='med'))

@@ -44,5 +44,17 @@ echo "== E probes"
 timeout 600 python tools/gpu_probe.py > $O/probe.log 2>&1; echo "rc=$?"; tail -30 $O/probe.log
 alive || stop "device does not answer after probes"
 timeout 600 python tools/next_rows_probe.py > $O/next_rows_probe.log 2>&1; echo "rc=$?"; tail -20 $O/next_rows_probe.log
+echo "== F opt-in kernels that have never run on a GPU (TMA-fed step kernel, tcgen05 KSD, tensor-memory row store):"
+echo "   each in its own process under its own timeout, memcheck first; every wait inside them is deadline-bounded"
+OPT='tests/test_zz_next_rows.py::test_tensor_core_and_tma_variants_on_device'
+GFK_TEST_OPTIN_KERNELS=1 timeout 900 compute-sanitizer --tool memcheck --print-limit 30 python -m pytest $OPT -m gpu -x -q --runxfail > $O/memcheck_optin.log 2>&1; echo "rc=$?"; tail -6 $O/memcheck_optin.log
+alive || stop "device does not answer after the opt-in kernels under memcheck"
+if clean $O/memcheck_optin.log; then
+    GFK_TEST_OPTIN_KERNELS=1 timeout 600 python -m pytest $OPT -m gpu -x -q --runxfail > $O/pytest_optin.log 2>&1; echo "rc=$?"; tail -6 $O/pytest_optin.log
+    alive || stop "device does not answer after the opt-in kernels"
+    AB_TAG=default timeout 200 python tools/ab_probe.py > $O/ab_tmem.log 2>&1; echo "rc=$?"
+    AB_TAG=tmem GFK_TMEM=1 timeout 200 python tools/ab_probe.py >> $O/ab_tmem.log 2>&1; echo "rc=$?"
+    tail -6 $O/ab_tmem.log
+fi
 nvidia-smi --query-gpu=index,name,clocks_throttle_reasons.active --format=csv >> $O/smi.log 2>&1
 echo "DONE"
