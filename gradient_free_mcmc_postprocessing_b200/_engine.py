@@ -336,14 +336,13 @@ class SteinProblem:
             diag = torch.empty(m, dtype=torch.float64, device=self.device)
             ks = torch.empty(m, dtype=torch.float64, device=self.device)
             # opt-in (GFK_KSD_MMA=1): the row sums on the tensor cores - float32 mode, scalar preconditioner,
-            # 32 <= d <= 64, one rank (csrc/ksd_mma.cuh; not yet measured on a GPU, hence not the default)
-            use_mma = (os.environ.get('GFK_KSD_MMA') == '1' and lib.gfk_comm_size() == 1
-                       and lib.gfk_ksd_mma_supported(ctypes.byref(self.struct)))
+            # 32 <= d <= 64 (csrc/ksd_mma.cuh; not yet measured on a GPU, hence not the default)
+            use_mma = (os.environ.get('GFK_KSD_MMA') == '1' and lib.gfk_ksd_mma_supported(ctypes.byref(self.struct)))
             if use_mma:
                 ws = _bytes(lib.gfk_ksd_mma_ws_bytes(m, self.d) + 256, self.device)
                 base = (ws.data_ptr() + 255) // 256 * 256
-                rc = lib.gfk_ksd_rowsums_mma(ctypes.byref(self.struct), _ptr(sel_dev), m, _ptr(low), _ptr(diag),
-                                             ctypes.c_void_p(base), st)
+                rc = lib.gfk_ksd_rowsums_mma(ctypes.byref(self.struct), _ptr(sel_dev), m, lib.gfk_comm_rank(),
+                                             lib.gfk_comm_size(), _ptr(low), _ptr(diag), ctypes.c_void_p(base), st)
                 if rc == _lib.GFK_EUNSUPPORTED:
                     use_mma = False                      # e.g. no cuTensorMapEncodeTiled in this driver
                 else:

@@ -73,7 +73,7 @@ PROTOTYPES = {
     'gfk_ksd_rowsums': (ctypes.c_int, [_pp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'gfk_ksd_mma_supported': (ctypes.c_int, [_pp]),
     'gfk_ksd_mma_ws_bytes': (_sz, [_i64, _i32]),
-    'gfk_ksd_rowsums_mma': (ctypes.c_int, [_pp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    'gfk_ksd_rowsums_mma': (ctypes.c_int, [_pp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     'gfk_ksd_mma_check': (ctypes.c_int, [_vp, _vp]),
     'gfk_ksd_finish': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'gfk_kmat': (ctypes.c_int, [_pp, _vp, _i64, _vp, _vp]),

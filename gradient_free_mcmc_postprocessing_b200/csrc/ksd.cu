@@ -39,6 +39,7 @@ struct KsdArgs {
     KParams kp;
     int wstride;        // elements between consecutive rows' weights in w: 1 (fast modes), 2 (strict: (hi, lo) pairs)
     int part, n_parts;
+    int deal_rows;      // rows per dealt tile: (t / deal_rows) % n_parts owns row t (TILE; 128 for the tensor-core kernel)
     double* low;
     double* diag;
 };
@@ -264,7 +265,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) ksd_diag_kernel(KsdArgs<T> a) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.m;
          t += (long long)gridDim.x * blockDim.x) {
-        const bool mine = ((t / TILE) % a.n_parts) == a.part;
+        const bool mine = ((t / a.deal_rows) % a.n_parts) == a.part;
         if (!mine) { a.low[t] = 0.0; a.diag[t] = 0.0; continue; }
         const long long i = row_of(a, t);
         const int d = a.kp.d;
@@ -377,6 +378,7 @@ static KsdArgs<T> make_args(const gfk_problem* p, const uint32_t* sel, int64_t m
     a.wstride = (p->mode == GFK_F64_STRICT) ? 2 : 1;
     a.part = 0;
     a.n_parts = 1;
+    a.deal_rows = TILE;
     a.low = nullptr;
     a.diag = nullptr;
     return a;
@@ -464,13 +466,14 @@ extern "C" size_t gfk_ksd_mma_ws_bytes(int64_t m, int32_t d) {
     return 512 + sizeof(double) * dp + 4 * sizeof(float) * mp * dp + 3 * sizeof(float) * mp + 1024;
 }
 
-extern "C" int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, int64_t m, double* low, double* diag,
-                                   void* ws, void* stream) {
+extern "C" int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, int64_t m, int32_t part, int32_t n_parts,
+                                   double* low, double* diag, void* ws, void* stream) {
     int rc = check_problem(p, "gfk_ksd_rowsums_mma");
     if (rc) return rc;
     GFK_REQUIRE(low && diag && ws && m >= 1, "gfk_ksd_rowsums_mma: bad arguments");
     GFK_REQUIRE(sel || m <= p->n, "gfk_ksd_rowsums_mma: m = %lld exceeds n = %lld", (long long)m, (long long)p->n);
     GFK_REQUIRE(m < 0x7fffff00LL, "gfk_ksd_rowsums_mma: m too large for 32-bit tensor-map coordinates");
+    GFK_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "gfk_ksd_rowsums_mma: bad part %d of %d", part, n_parts);
     if (!gfk_ksd_mma_supported(p)) {
         set_error("gfk_ksd_rowsums_mma: needs the float32 mode, a scalar preconditioner and 32 <= d <= 64");
         return GFK_EUNSUPPORTED;
@@ -496,6 +499,9 @@ extern "C" int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, in
     KsdArgs<float> a = make_args<float>(p, sel, m);
     a.low = low;
     a.diag = diag;
+    a.part = part;
+    a.n_parts = n_parts;
+    a.deal_rows = MM_M;                                  // 128-row tiles are dealt round-robin over the parts
     GFK_CUDA(cudaMemsetAsync(status, 0, 256, st));
     ksd_diag_kernel<float><<<grid1d(m), 256, 0, st>>>(a);
     ksd_mma_colmean_kernel<><<<d, 256, 0, st>>>(x, sel, m, d, mean);
@@ -518,10 +524,16 @@ extern "C" int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, in
     ma.kp = a.kp;
     ma.low = low;
     ma.status = status;
+    ma.part = part;
+    ma.n_parts = n_parts;
     const size_t smem = ksd_mma_smem_bytes(nkb);
-    GFK_CUDA(cudaFuncSetAttribute(ksd_mma_kernel<>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ksd_mma_kernel<><<<(unsigned)(mp / MM_M), MM_THREADS, smem, st>>>(ma, maps[0], maps[1], maps[2], maps[3]);
-    count_launches(4);
+    const long long ntiles = mp / MM_M;
+    const long long my_tiles = (ntiles - part + n_parts - 1) / n_parts;
+    if (my_tiles > 0) {
+        GFK_CUDA(cudaFuncSetAttribute(ksd_mma_kernel<>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ksd_mma_kernel<><<<(unsigned)my_tiles, MM_THREADS, smem, st>>>(ma, maps[0], maps[1], maps[2], maps[3]);
+    }
+    count_launches(my_tiles > 0 ? 4 : 3);
     GFK_CHECK_LAUNCH();
     return GFK_OK;
 }

@@ -47,6 +47,7 @@ struct KsdMmaArgs {
     const float* w;       // exp(lw) per selected row, or nullptr
     long long m;          // selected rows
     int nkb;              // K blocks (dp / 32)
+    int part, n_parts;    // this launch computes the 128-row tiles I with I % n_parts == part (ranks split the triangle)
     KParams kp;
     double* low;
     unsigned* status;     // device word, zeroed by the host entry; 1: a pipeline wait timed out (results invalid)
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
     unsigned char* col_ring = row_tiles + (size_t)4 * nkb * MM_ROW_TILE_BYTES;      // stage st, array a -> (st * 4 + a) tiles
 
     const long long ntiles = (a.m + MM_M - 1) / MM_M;
-    const long long I = ntiles - 1 - (long long)blockIdx.x;                         // largest (most column tiles) first
+    const long long my_tiles = (ntiles - a.part + a.n_parts - 1) / a.n_parts;       // == gridDim.x
+    const long long I = a.part + (my_tiles - 1 - (long long)blockIdx.x) * a.n_parts;   // this part's tiles, largest first
     const long long t0 = I * MM_M;
     long long nJ = (t0 + MM_M - 1 + MM_N - 1) / MM_N;                               // column tiles holding some b < t
     const long long nJ_all = (a.m + MM_N - 1) / MM_N;

@@ -225,7 +225,7 @@ int gfk_thin_batched_check(const void* ws, int32_t n_chains, void* stream);
 int gfk_ksd_rowsums(const gfk_problem* p, const uint32_t* sel, int64_t m, int32_t part,
                     int32_t n_parts, double* low, double* diag, void* stream);
 int gfk_ksd_finish(const double* low, const double* diag, int64_t m, double* ks, void* stream);
-/* The same row sums (low, diag as gfk_ksd_rowsums with n_parts = 1) on the tensor cores - BASELINE.json config 5, "for
+/* The same row sums (low, diag as gfk_ksd_rowsums, except that the tiles dealt over the parts are 128 rows) on the tensor cores - BASELINE.json config 5, "for
  * large d the cross terms are GEMM-shaped": the four Gram tiles X X', X S', S X', S S' (report/report.tex:853-868) by
  * tcgen05.mma kind::tf32 with 3xTF32 operand splits (22 significant bits), operands fed by TMA, accumulators in
  * tensor memory, the pair epilogue of the tile kernel on top.  float32 mode only (1e-5 relative on KSD values), scalar
@@ -234,8 +234,8 @@ int gfk_ksd_finish(const double* low, const double* diag, int64_t m, double* ks,
  * [round 2: executed on the CPU emulator of the test suite only, not yet on a GPU; opt-in from Python, GFK_KSD_MMA=1] */
 int gfk_ksd_mma_supported(const gfk_problem* p);
 size_t gfk_ksd_mma_ws_bytes(int64_t m, int32_t d);
-int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, int64_t m, double* low, double* diag, void* ws,
-                        void* stream);
+int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, int64_t m, int32_t part, int32_t n_parts, double* low,
+                        double* diag, void* ws, void* stream);
 /* SYNCHRONOUS, after gfk_ksd_rowsums_mma on the same stream and workspace: GFK_ECUDA if a wait inside the kernel's
  * producer / MMA / epilogue pipeline ran past its 2 s deadline (the kernel then terminated with invalid sums) */
 int gfk_ksd_mma_check(const void* ws, void* stream);

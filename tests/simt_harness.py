@@ -219,7 +219,7 @@ class SimProblem:
         check(lib.gfk_ksd_rowsums(ctypes.byref(self.struct), ptr(sel_dev), m, part, n_parts, ptr(low), ptr(diag), None))
         return low.copy(), diag.copy()
 
-    def ksd_rowsums_mma(self, sel=None, m=None):
+    def ksd_rowsums_mma(self, sel=None, m=None, part=0, n_parts=1):
         """gfk_ksd_rowsums_mma (tensor-core row sums); None when the problem is not eligible."""
         lib = load()
         if not lib.gfk_ksd_mma_supported(ctypes.byref(self.struct)):
@@ -229,7 +229,8 @@ class SimProblem:
         low, diag = guarded((m,), np.float64, fill=np.nan), guarded((m,), np.float64, fill=np.nan)
         raw = guarded((lib.gfk_ksd_mma_ws_bytes(m, self.d) + 256,), np.uint8, fill=0xa5)
         base = (raw.ctypes.data + 255) // 256 * 256
-        check(lib.gfk_ksd_rowsums_mma(ctypes.byref(self.struct), ptr(sel_dev), m, ptr(low), ptr(diag), ctypes.c_void_p(base), None))
+        check(lib.gfk_ksd_rowsums_mma(ctypes.byref(self.struct), ptr(sel_dev), m, part, n_parts, ptr(low), ptr(diag),
+                                      ctypes.c_void_p(base), None))
         check(lib.gfk_ksd_mma_check(ctypes.c_void_p(base), None))
         return low.copy(), diag.copy()
 

@@ -17,8 +17,8 @@ STRATEGY_ENVS = [{}, {'GFK_RESIDENT': '0'}, {'GFK_PERSISTENT': '0'}]
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(2, 1400), d=st.integers(1, 12), m=st.integers(1, 24),
        dup=st.sampled_from([0.0, 0.3, 0.8]), pre=st.sampled_from(['id', 'med', 'sclmed', '0.7']), gf=st.booleans(),
        strategy=st.integers(0, 2), sms=st.integers(1, 6), fast=st.booleans(), scale=st.sampled_from([1e-3, 1.0, 50.0]),
-       tmem=st.booleans())
-def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fast, scale, tmem):
+       tmem=st.booleans(), tma=st.booleans())
+def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fast, scale, tmem, tma):
     rng = np.random.default_rng(seed)
     base = rng.standard_normal((n, d)) * scale + rng.standard_normal(d)
     keep = rng.random(n) > dup
@@ -34,6 +34,7 @@ def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fas
     os.environ.update(STRATEGY_ENVS[strategy])
     os.environ['SIMT_SMS'] = str(sms)
     os.environ['GFK_TMEM'] = '1' if tmem else '0'          # opt-in tensor-memory row store (d = 2, 4 only)
+    os.environ['GFK_STEP_TMA'] = '1' if tma else '0'       # opt-in TMA-fed step kernel (d > 4, even d, launch per step)
     H.set_schedule(False)
     precision = 'f64-fast' if fast else 'f64'
     try:
@@ -70,7 +71,7 @@ def test_thinning_matches_oracle(seed, n, d, m, dup, pre, gf, strategy, sms, fas
                    else ot._make_stein_integrand(x, g, preconditioner=pre))
             np.testing.assert_allclose(p.ksd(), os_.ksd(ref, n), rtol=1e-10)
     finally:
-        for k in ('GFK_PERSISTENT', 'GFK_RESIDENT', 'SIMT_SMS', 'GFK_TMEM'):
+        for k in ('GFK_PERSISTENT', 'GFK_RESIDENT', 'SIMT_SMS', 'GFK_TMEM', 'GFK_STEP_TMA'):
             os.environ.pop(k, None)
 
 

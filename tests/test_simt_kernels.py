@@ -732,6 +732,10 @@ def test_tensor_core_ksd_row_sums(d):
         low2, _ = p.ksd_rowsums_mma()
         assert np.array_equal(low2, low), gf
         H.set_schedule(False)
+        # the triangle dealt over three parts (128-row tiles round-robin): the parts' vectors add up to the whole
+        parts = [p.ksd_rowsums_mma(part=k, n_parts=3) for k in range(3)]
+        assert np.array_equal(sum(q[0] for q in parts), low) and np.array_equal(sum(q[1] for q in parts), diag)
+        assert all(np.count_nonzero(q[1]) <= 128 for q in parts)
         sel = rng.integers(0, n, 200)
         lo_s, dg_s = p.ksd_rowsums_mma(sel=sel)
         np.testing.assert_allclose(p.ksd_from_rowsums(lo_s, dg_s), os_.ksd(lambda i, j: ref(sel[i], sel[j]), 200), rtol=1e-5)
