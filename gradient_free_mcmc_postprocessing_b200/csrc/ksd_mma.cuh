@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
             for (long long q = 0; q < nJ * nkb; ++q) {
                 const int st = (int)(q % MM_RING);
                 const long long use = q / MM_RING;
-                if (use > 0) dev_mbar_wait(&col_empty[st], (unsigned)((use - 1) & 1), a.status);      // the MMAs that read it are done
+                if (use > 0 && !dev_mbar_wait(&col_empty[st], (unsigned)((use - 1) & 1), a.status)) break;   // the MMAs that read it are done
                 const long long J = q / nkb;
                 const int kb = (int)(q - J * nkb);
                 dev_mbar_arrive_expect_tx(&col_full[st], 4u * MM_COL_TILE_BYTES);
@@ -254,17 +254,17 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
         // (a lane that only polled a barrier its warp-mate acts on could miss a phase: the elected lane's commit lets
         //  the producer refill the stage, and two completions later the parity looks unfinished again)
         if (lane == 0) {
-            dev_mbar_wait(&row_full, 0, a.status);
-            for (long long J = 0; J < nJ; ++J) {
+            bool alive = dev_mbar_wait(&row_full, 0, a.status);
+            for (long long J = 0; alive && J < nJ; ++J) {
                 const int ab = (int)(J & 1);
                 const long long useA = J >> 1;
-                if (useA > 0) dev_mbar_wait(&acc_empty[ab], (unsigned)((useA - 1) & 1), a.status);    // the epilogue has drained it
+                if (useA > 0 && !dev_mbar_wait(&acc_empty[ab], (unsigned)((useA - 1) & 1), a.status)) break;   // the epilogue has drained it
                 dev_tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(ab * MM_ACC_COLS);
                 for (int kb = 0; kb < nkb; ++kb) {
                     const long long q = J * nkb + kb;
                     const int st = (int)(q % MM_RING);
-                    dev_mbar_wait(&col_full[st], (unsigned)((q / MM_RING) & 1), a.status);            // this K block of column tile J landed
+                    if (!dev_mbar_wait(&col_full[st], (unsigned)((q / MM_RING) & 1), a.status)) { alive = false; break; }   // K block landed
                     dev_tc_fence_after();
                     const unsigned r_xh = dev_smem_u32(row_tiles + (size_t)(0 * nkb + kb) * MM_ROW_TILE_BYTES);
                     const unsigned r_xl = dev_smem_u32(row_tiles + (size_t)(1 * nkb + kb) * MM_ROW_TILE_BYTES);
@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
         double rowacc = 0.0;
         for (long long J = 0; J < nJ; ++J) {
             const int ab = (int)(J & 1);
-            dev_mbar_wait(&acc_full[ab], (unsigned)((J >> 1) & 1), a.status);
+            // warp-uniform verdict: the tcgen05.ld below are .sync.aligned, a warp must leave the loop together
+            if (!__all_sync(0xffffffffu, dev_mbar_wait(&acc_full[ab], (unsigned)((J >> 1) & 1), a.status))) break;
             dev_tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * MM_ACC_COLS);
 #pragma unroll 1

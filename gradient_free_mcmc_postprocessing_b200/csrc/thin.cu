@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) thin_step_tma_kernel(ThinArgs<
             for (long long q = 0; q < nstages; ++q) {
                 const int st = (int)(q % kTmaStages);
                 const long long use = q / kTmaStages;                       // how often this buffer was filled before
-                if (use > 0) dev_mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1), &a.ws->abort);   // its previous contents are consumed
+                if (use > 0 && !dev_mbar_wait(&empty_bar[st], (unsigned)((use - 1) & 1), &a.ws->abort)) break;   // previous contents consumed
                 const long long it = q / nslabs;
                 const int k0 = (int)(q - it * nslabs) * KS;
                 const long long row0 = a.row_begin + first + it * stride;       // global row of the tile's first row
@@ -897,7 +897,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) thin_step_tma_kernel(ThinArgs<
         const unsigned r7 = threadIdx.x & 7u;
         for (long long q = 0; q < nstages; ++q) {
             const int st = (int)(q % kTmaStages);
-            dev_mbar_wait(&full_bar[st], (unsigned)((q / kTmaStages) & 1), &a.ws->abort);   // both tiles of slab q have landed
+            // both tiles of slab q have landed; the verdict is made warp-uniform so that a warp leaves the loop together
+            if (!__all_sync(0xffffffffu, dev_mbar_wait(&full_bar[st], (unsigned)((q / kTmaStages) & 1), &a.ws->abort))) break;
             const long long it = q / nslabs;
             const int slab = (int)(q - it * nslabs);
             const int k0 = slab * KS;

@@ -7,6 +7,7 @@
 #if !defined(GFK_SIMT_HOST)
 #include <cuda.h>      // CUtensorMap and its enums only
 #endif
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -24,7 +25,16 @@ __device__ __forceinline__ bool dev_mbar_try(unsigned long long* bar, unsigned p
     simt::poll_yield();
     return false;
 }
-constexpr unsigned long long kMbarWaitLimitNs = 120ull * 1000000000ull;     // emulated CTAs are slow
+// emulated CTAs are slow: 120 s, or SIMT_MBAR_LIMIT_MS for the fault-injection tests
+static inline unsigned long long mbar_wait_limit_ns() {
+    static unsigned long long v = 0;
+    if (!v) {
+        const char* e = getenv("SIMT_MBAR_LIMIT_MS");
+        v = (e && atof(e) > 0.0) ? (unsigned long long)(atof(e) * 1e6) : 120ull * 1000000000ull;
+    }
+    return v;
+}
+#define kMbarWaitLimitNs (gfk::mbar_wait_limit_ns())
 __device__ __forceinline__ void dev_tma_load_2d(void* dst, const TensorMap* map, int c0, int c1, unsigned long long* bar) {
     simt::tma_load_2d(dst, map, c0, c1, bar);
 }
@@ -64,19 +74,21 @@ __device__ __forceinline__ void dev_tma_load_2d(void* dst, const TensorMap* map,
 // Wait for the phase with this parity, BOUNDED: these barriers only connect warps of one CTA (and its copy / tensor
 // engines), so a wait that lasts seconds means a defect, not a slow peer - the waiter then raises *abort_flag (device
 // memory; the host entry's check call reports it as GFK_ECUDA) and every later wait of the kernel returns at once, so
-// the kernel always terminates instead of hanging the GPU.  Results of an aborted launch are garbage, never addresses.
-__device__ __forceinline__ void dev_mbar_wait(unsigned long long* bar, unsigned parity, unsigned* abort_flag) {
-    if (dev_mbar_try(bar, parity)) return;
+// the kernel always terminates instead of hanging the GPU.  Returns false when the launch is aborted: the caller leaves
+// its loop (no further arrivals or copies on barriers whose phases will never complete).  Results of an aborted launch
+// are garbage, never addresses.
+__device__ __forceinline__ bool dev_mbar_wait(unsigned long long* bar, unsigned parity, unsigned* abort_flag) {
+    if (dev_mbar_try(bar, parity)) return true;
     unsigned long long t0 = 0;
     unsigned tries = 0;
 #pragma unroll 1
     for (;;) {
-        if (dev_mbar_try(bar, parity)) return;
+        if (dev_mbar_try(bar, parity)) return true;
+        if (*reinterpret_cast<volatile unsigned*>(abort_flag)) return false;   // slow path only: the first try already failed
         if ((++tries & 255u) == 0u) {
-            if (*reinterpret_cast<volatile unsigned*>(abort_flag)) return;
             const unsigned long long now = gfk_timer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > kMbarWaitLimitNs) { *reinterpret_cast<volatile unsigned*>(abort_flag) = 1u; return; }
+            else if (now - t0 > kMbarWaitLimitNs) { *reinterpret_cast<volatile unsigned*>(abort_flag) = 1u; return false; }
         }
     }
 }

@@ -96,6 +96,7 @@ struct Block {
     unsigned polls = 0;
     struct PendingTma { void* dst; TensorMap2D map; int c0, c1; unsigned long long* bar; };
     std::vector<PendingTma> tma;        // bulk tensor copies issued and not yet completed
+    bool fault_injected = false;        // tests lost a copy on purpose: leftovers at exit are expected
     unsigned long long mbar_polls = 0;  // consecutive unsuccessful mbarrier tests (a wait that can never complete)
     std::vector<unsigned> tmem;         // 128 lanes x 512 columns once allocated
     int tmem_cols = 0;                  // allocated columns (0: none)
@@ -315,6 +316,7 @@ void cp_async_wait(int allow_pending_groups) {
 
 static std::atomic<long long> g_tma_loads{0};
 static std::atomic<long long> g_umma_issued{0};
+static std::atomic<long long> g_tma_drop{-1};     // index (in issue order) of a bulk copy to lose, tests only
 
 // shared-window address of a pointer into dynamic shared memory (what cvta.to.shared gives on the device)
 unsigned smem_u32(const void* p) {
@@ -478,14 +480,17 @@ void tma_load_2d(void* dst, const TensorMap2D* map, int c0, int c1, unsigned lon
     }
     const size_t bytes = (size_t)map->box0 * map->elem * map->box1;
     if (static_cast<char*>(dst) < b->smem) fail("cp.async.bulk.tensor destination outside dynamic shared memory");
-    g_tma_loads.fetch_add(1, std::memory_order_relaxed);
-    memset(dst, 0xff, bytes);                                    // not there yet: a reader that does not wait sees NaNs
+    const long long nth = g_tma_loads.fetch_add(1, std::memory_order_relaxed);
+    memset(dst, 0xff, bytes);
+    if (g_tma_drop.load() == nth) { b->fault_injected = true; return; }   // fault injection: this copy never completes                                    // not there yet: a reader that does not wait sees NaNs
     b->tma.push_back(Block::PendingTma{dst, *map, c0, c1, bar});
 }
 
 }  // namespace simt
 extern "C" long long simt_tma_loads() { return simt::g_tma_loads.load(); }
-extern "C" long long simt_umma_issued() { return simt::g_umma_issued.load(); }   // tests: did the TMA kernel run at all?
+extern "C" long long simt_umma_issued() { return simt::g_umma_issued.load(); }
+// the bulk tensor copy issued `after` copies from now is silently lost (its bytes never arrive); -1 switches it off
+extern "C" void simt_drop_tma(long long after) { simt::g_tma_drop.store(after < 0 ? -1 : simt::g_tma_loads.load() + after); }   // tests: did the TMA kernel run at all?
 namespace simt {
 unsigned long long now_ns() {
     struct timespec ts;
@@ -566,6 +571,7 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
     for (NamedBarrier& nb : b.named) nb = NamedBarrier();
     b.tmem_cols = 0;
     b.tma.clear();
+    b.fault_injected = false;
     b.mbar_polls = 0;
     if (smem_bytes) memset(b.smem, 0xff, smem_bytes);   // poison: NaN patterns / huge integers
     uint3 bid;
@@ -637,7 +643,7 @@ static void run_block(Block& b, char* stacks, unsigned linear_block, dim3 grid, 
         simt_switch(&b.sched_sp, f.sp);
         b.running = nullptr;
     }
-    if (!b.failed && !b.tma.empty()) {
+    if (!b.failed && !b.tma.empty() && !b.fault_injected) {
         record_error("block exited with cp.async.bulk.tensor copies in flight (nobody waited for their mbarrier)");
         b.tma.clear();
     }

@@ -189,6 +189,14 @@ inline int __any_sync(unsigned mask, int pred) {
         if (((alive >> l) & 1u) && all[l]) return 1;
     return 0;
 }
+inline int __all_sync(unsigned mask, int pred) {
+    (void)mask;
+    const unsigned long long* all = simt::warp_gather(pred ? 1ull : 0ull);
+    const unsigned alive = simt::warp_alive_mask();
+    for (int l = 0; l < 32; ++l)
+        if (((alive >> l) & 1u) && !all[l]) return 0;
+    return 1;
+}
 inline unsigned __ballot_sync(unsigned mask, int pred) {
     (void)mask;
     const unsigned long long* all = simt::warp_gather(pred ? 1ull : 0ull);

@@ -745,6 +745,59 @@ def test_tensor_core_ksd_row_sums(d):
     assert H.SimProblem(xs, gs, preconditioner='med', precision='f32').ksd_rowsums_mma() is None
 
 
+def test_a_lost_bulk_copy_ends_in_an_error_not_in_a_hang(monkeypatch):
+    """The mbarrier waits of the TMA-fed step kernel and of the tensor-core KSD are bounded (csrc/tma.cuh dev_mbar_wait):
+    if the bytes a barrier expects never arrive, the waiter raises the launch's abort flag after its deadline, every
+    other wait of the kernel returns at once, the kernel terminates (tensor memory freed, no barrier left hanging) and
+    the check call reports GFK_ECUDA.  The emulator loses one chosen bulk copy; run in a subprocess because the
+    deadline is read once per process."""
+    import subprocess
+    import sys
+    code = '''
+import ctypes, os, sys, time
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import simt_harness as H
+rng = np.random.default_rng(3)
+x = rng.standard_normal((900, 64)); g = -x
+lib = H.load()
+lib.simt_drop_tma.argtypes = [ctypes.c_longlong]
+os.environ["GFK_PERSISTENT"] = "0"; os.environ["GFK_STEP_TMA"] = "1"; os.environ["SIMT_SMS"] = "2"
+p = H.SimProblem(x, g, preconditioner="med")
+good = p.thin(4)[0]
+for which, after in (("step", 5), ("step", 0)):
+    lib.simt_drop_tma(after)
+    t0 = time.time()
+    try:
+        p.thin(4)
+    except H.SimError as e:
+        assert "deadline" in str(e), str(e)
+    else:
+        raise AssertionError("a lost copy went unnoticed")
+    assert time.time() - t0 < 60
+lib.simt_drop_tma(-1)
+assert np.array_equal(p.thin(4)[0], good)                 # the next job is unaffected
+q = H.SimProblem(x[:400], g[:400], preconditioner="med", precision="f32")
+ok = q.ksd_rowsums_mma()
+for after in (0, 9, 20):                                  # a row operand, a column tile of the first / a later stage
+    lib.simt_drop_tma(after)
+    try:
+        q.ksd_rowsums_mma()
+    except H.SimError as e:
+        assert "deadline" in str(e), str(e)
+    else:
+        raise AssertionError("a lost copy went unnoticed")
+lib.simt_drop_tma(-1)
+again = q.ksd_rowsums_mma()
+assert np.array_equal(again[0], ok[0])
+print("LOST_COPY_OK")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    H.load()
+    env = dict(os.environ, SIMT_MBAR_LIMIT_MS='1500')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and 'LOST_COPY_OK' in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
 def test_full_size_c3_on_the_b200_grid_shape(monkeypatch):
     """BASELINE config C3 at full size (n = 10^6, d = 4, gradient-free, 'med') with the launch geometry of a B200:
     148 concurrently running CTAs of 512 threads, 14 rows per thread of which 3 stay in shared memory, every CTA
