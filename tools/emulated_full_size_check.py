@@ -2,7 +2,7 @@
 geometry against the committed oracle sequences (tests/golden/full_size_indices.npz).  No GPU involved; a prediction of
 what the device returns, not a measurement.
 
-    python tools/emulated_full_size_check.py c5 [GFK_STEP_TMA=1 ...]      # c2 | c3 | c5, then environment settings
+    python tools/emulated_full_size_check.py c5 [GFK_STEP_TMA=1 ...]      # c2 | c3 | c5 | chains5, then environment settings
 """
 import os
 import sys
@@ -24,6 +24,24 @@ from gradient_free_mcmc_postprocessing_b200 import synthetic  # noqa: E402
 
 warnings.simplefilter('ignore')
 which = sys.argv[1]
+if which == 'chains5':
+    # five C2-shaped chains of 2 x 10^5 rows in ONE batched launch at the B200 geometry (29 CTAs per chain) against one
+    # job per chain (148 CTAs each) - the first 120 greedy steps
+    m = 120
+    probs = []
+    for i in range(5):
+        c = synthetic.config_c2(seed=12345 + i, m=m)
+        probs.append(H.SimProblem(c['sample'], c['gradient'], preconditioner='med'))
+    t = time.time()
+    single = [p.thin(m) for p in probs]
+    t1 = time.time() - t
+    t = time.time()
+    got = H.thin_batched(probs, m)
+    same = got is not None and all(np.array_equal(got[0][i], single[i][0]) and np.array_equal(got[1][i], single[i][1])
+                                   for i in range(5))
+    print('chains5 emulated: one job per chain %.1f s, batched %.1f s, indices and objectives identical: %s' %
+          (t1, time.time() - t, same), flush=True)
+    sys.exit(0 if same else 1)
 golden = np.load(os.path.join(ROOT, 'tests', 'golden', 'full_size_indices.npz'))
 c = synthetic.CONFIGS[which]()
 t = time.time()

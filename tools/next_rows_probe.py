@@ -62,6 +62,21 @@ for prec in ('f64', 'f64-fast', 'f32'):
     os.environ.pop('GFK_STEP_TMA', None)
 del p
 
+# large-d KSD in the float32 mode: SIMT tile kernel vs the tensor-core kernel (opt-in GFK_KSD_MMA=1), d = 64
+rng5 = np.random.default_rng(5)
+for n5 in (50_000, 200_000):
+    x5 = torch.from_numpy(rng5.standard_normal((n5, 64)) + 1.0).cuda()
+    g5 = -(x5 - 1.0) / 8.0
+    p5 = SteinProblem(x5, g5, preconditioner='med', precision='f32')
+    pairs5 = n5 * (n5 + 1) / 2
+    for mma in ('0', '1'):
+        os.environ['GFK_KSD_MMA'] = mma
+        ks5 = p5.ksd(None, 10_000)
+        t = timed(lambda: p5.ksd(None, n5), reps=2)
+        note(f'ksd_d64_f32:{n5}:mma{mma}', seconds=t, pair_evals_per_s=pairs5 / t, ks_10k=float(ks5[-1]))
+    os.environ.pop('GFK_KSD_MMA', None)
+    del p5
+
 # section 8f kernels
 rng = np.random.default_rng(0)
 for n, d in ((100_000, 4), (200_000, 2)):
