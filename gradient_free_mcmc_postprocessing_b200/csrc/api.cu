@@ -119,6 +119,7 @@ extern "C" int gfk_fma_peak(int is_f32, double* tflops_host, void* stream) {
 
 extern "C" int gfk_flush_l2(void* scratch, size_t bytes, void* stream) {
     GFK_REQUIRE(scratch && bytes >= 16, "gfk_flush_l2: bad arguments");
+    GFK_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 16 == 0, "gfk_flush_l2: scratch must be 16-byte aligned (vector stores)");
     flush_kernel<<<sm_count() * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(scratch),
                                                                                bytes / 16);
     count_launches(1);

@@ -457,7 +457,7 @@ static inline long long mma_pad_rows(long long m) { return (m + MM_M - 1) / MM_M
 static inline int mma_pad_dims(int d) { return (d + MM_KB - 1) / MM_KB * MM_KB; }
 
 extern "C" int gfk_ksd_mma_supported(const gfk_problem* p) {
-    return (p && p->mode == GFK_F32_FAST && !p->xl && p->d >= 32 && p->d <= 64) ? 1 : 0;
+    return (p && p->mode == GFK_F32_FAST && !p->xl && p->d >= 32 && p->d <= 512) ? 1 : 0;
 }
 
 extern "C" size_t gfk_ksd_mma_ws_bytes(int64_t m, int32_t d) {
@@ -475,7 +475,7 @@ extern "C" int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, in
     GFK_REQUIRE(m < 0x7fffff00LL, "gfk_ksd_rowsums_mma: m too large for 32-bit tensor-map coordinates");
     GFK_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "gfk_ksd_rowsums_mma: bad part %d of %d", part, n_parts);
     if (!gfk_ksd_mma_supported(p)) {
-        set_error("gfk_ksd_rowsums_mma: needs the float32 mode, a scalar preconditioner and 32 <= d <= 64");
+        set_error("gfk_ksd_rowsums_mma: needs the float32 mode, a scalar preconditioner and 32 <= d <= 512");
         return GFK_EUNSUPPORTED;
     }
     GFK_REQUIRE(reinterpret_cast<uintptr_t>(ws) % 256 == 0, "gfk_ksd_rowsums_mma: ws must be 256-byte aligned");
@@ -530,8 +530,13 @@ extern "C" int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, in
     const long long ntiles = mp / MM_M;
     const long long my_tiles = (ntiles - part + n_parts - 1) / n_parts;
     if (my_tiles > 0) {
-        GFK_CUDA(cudaFuncSetAttribute(ksd_mma_kernel<>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ksd_mma_kernel<><<<(unsigned)my_tiles, MM_THREADS, smem, st>>>(ma, maps[0], maps[1], maps[2], maps[3]);
+        if (nkb <= MM_RESIDENT_MAX_KB) {
+            GFK_CUDA(cudaFuncSetAttribute(ksd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ksd_mma_kernel<true><<<(unsigned)my_tiles, MM_THREADS, smem, st>>>(ma, maps[0], maps[1], maps[2], maps[3]);
+        } else {
+            GFK_CUDA(cudaFuncSetAttribute(ksd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ksd_mma_kernel<false><<<(unsigned)my_tiles, MM_THREADS, smem, st>>>(ma, maps[0], maps[1], maps[2], maps[3]);
+        }
     }
     count_launches(my_tiles > 0 ? 4 : 3);
     GFK_CHECK_LAUNCH();

@@ -8,14 +8,14 @@
 //     <s_i, s_j>
 // i.e. four tile GEMMs  G1 = X X',  G2 = X S',  G3 = S X',  G4 = S S'  plus per-row scalars; everything after the dot
 // products (powers of the quadratic form, weights, triangular mask, row sums) is the epilogue of ksd_rowsum_kernel.
-// This is the float32 mode of the path (1e-5 relative on KSD values, BASELINE.json), for 32 <= d <= 64:
+// This is the float32 mode of the path (1e-5 relative on KSD values, BASELINE.json), for 32 <= d <= 512:
 //
 //   * operands: tcgen05.mma kind::tf32 keeps 11 significant bits of an operand, far short of 1e-5, so every value
 //     is split v = hi + lo (hi = tf32(v), lo = tf32(v - hi): 22 bits together) by a prep kernel and a product is
 //     hi hi' + hi lo' + lo hi' ("3xTF32"; the dropped lo lo' term is 2^-22 relative).  x is centred first (both
 //     expansions above are invariant under a common shift of x), which keeps the cancellation in the first one small.
-//   * a CTA of six warps owns a 128-row tile: warp 0 is the TMA producer (the four split row operands stay resident in
-//     shared memory, column tiles of 64 rows stream through a two-buffer ring, one 128-byte K block per stage, all as
+//   * a CTA of six warps owns a 128-row tile: warp 0 is the TMA producer (for d <= 64 the four split row operands stay
+//     resident in shared memory - beyond that their K blocks stream with the column tiles' -, column tiles of 64 rows stream through a two-buffer ring, one 128-byte K block per stage, all as
 //     SWIZZLE_128B K-major tiles - exactly what a UMMA shared-memory descriptor addresses), warp 1 allocates tensor
 //     memory and one of its lanes issues the MMAs (M = 128, N = 64, K = 8: 12 per K step), warps 2-5 are the epilogue:
 //     thread r reads row r of the four accumulators from tensor memory with tcgen05.ld and finishes its 64 pairs.
@@ -192,7 +192,10 @@ __device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr
 // A / B major 0 = K, [17,23) N >> 3, [24,29) M >> 4
 constexpr unsigned kUmmaIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(MM_N >> 3) << 17) | ((unsigned)(MM_M >> 4) << 24);
 
-template <typename Dummy = void>
+// RESIDENT: the four row operands stay in shared memory for the whole tile (d <= 64: 4 arrays x nkb x 16 KB) and only
+// column tiles stream; otherwise (64 < d <= 512) a ring stage carries the K block of BOTH the row and the column
+// operands (96 KB per stage) - the row tile is then re-read once per column tile, which only L2 makes affordable.
+template <bool RESIDENT>
 __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, const __grid_constant__ TensorMap map_xh,
                                                                 const __grid_constant__ TensorMap map_xl,
                                                                 const __grid_constant__ TensorMap map_sh,
@@ -201,9 +204,18 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
     __shared__ __align__(8) unsigned long long row_full, col_full[MM_RING], col_empty[MM_RING], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_sh;
     const int nkb = a.nkb;
-    // [1024-byte aligned] row operands: array a (xh, xl, sh, sl), K block kb -> tile (a * nkb + kb); then the column ring
-    unsigned char* row_tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mm_smem) + 1023u) & ~(uintptr_t)1023u);
-    unsigned char* col_ring = row_tiles + (size_t)4 * nkb * MM_ROW_TILE_BYTES;      // stage st, array a -> (st * 4 + a) tiles
+    // RESIDENT: [1024-byte aligned] row operands: array arr (xh, xl, sh, sl), K block kb -> tile (arr * nkb + kb); then the
+    // column ring: stage st, array arr -> tile (st * 4 + arr).  Streaming: stage st = { 4 row tiles, 4 column tiles }.
+    unsigned char* smem0 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mm_smem) + 1023u) & ~(uintptr_t)1023u);
+    constexpr size_t kStageBytes = RESIDENT ? (size_t)4 * MM_COL_TILE_BYTES : (size_t)4 * (MM_ROW_TILE_BYTES + MM_COL_TILE_BYTES);
+    unsigned char* ring = RESIDENT ? smem0 + (size_t)4 * nkb * MM_ROW_TILE_BYTES : smem0;
+    auto row_tile = [&](int st, int arr, int kb) -> unsigned char* {
+        return RESIDENT ? smem0 + (size_t)(arr * nkb + kb) * MM_ROW_TILE_BYTES
+                        : ring + (size_t)st * kStageBytes + (size_t)arr * MM_ROW_TILE_BYTES;
+    };
+    auto col_tile = [&](int st, int arr) -> unsigned char* {
+        return ring + (size_t)st * kStageBytes + (RESIDENT ? 0 : (size_t)4 * MM_ROW_TILE_BYTES) + (size_t)arr * MM_COL_TILE_BYTES;
+    };
 
     const long long ntiles = (a.m + MM_M - 1) / MM_M;
     const long long my_tiles = (ntiles - a.part + a.n_parts - 1) / a.n_parts;       // == gridDim.x
@@ -230,22 +242,28 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
     if (warp == 0) {
         // ---- TMA producer -----------------------------------------------------------------------------------
         if (lane == 0) {
-            dev_mbar_arrive_expect_tx(&row_full, 4u * (unsigned)nkb * MM_ROW_TILE_BYTES);
-            for (int arr = 0; arr < 4; ++arr)
-                for (int kb = 0; kb < nkb; ++kb)
-                    for (int half = 0; half < MM_M / MM_N; ++half)
-                        dev_tma_load_2d(row_tiles + (size_t)(arr * nkb + kb) * MM_ROW_TILE_BYTES + (size_t)half * MM_COL_TILE_BYTES,
-                                        maps[arr], kb * MM_KB, (int)(t0 + half * MM_N), &row_full);
+            if (RESIDENT) {
+                dev_mbar_arrive_expect_tx(&row_full, 4u * (unsigned)nkb * MM_ROW_TILE_BYTES);
+                for (int arr = 0; arr < 4; ++arr)
+                    for (int kb = 0; kb < nkb; ++kb)
+                        for (int half = 0; half < MM_M / MM_N; ++half)
+                            dev_tma_load_2d(row_tile(0, arr, kb) + (size_t)half * MM_COL_TILE_BYTES, maps[arr], kb * MM_KB,
+                                            (int)(t0 + half * MM_N), &row_full);
+            }
             for (long long q = 0; q < nJ * nkb; ++q) {
                 const int st = (int)(q % MM_RING);
                 const long long use = q / MM_RING;
                 if (use > 0 && !dev_mbar_wait(&col_empty[st], (unsigned)((use - 1) & 1), a.status)) break;   // the MMAs that read it are done
                 const long long J = q / nkb;
                 const int kb = (int)(q - J * nkb);
-                dev_mbar_arrive_expect_tx(&col_full[st], 4u * MM_COL_TILE_BYTES);
-                for (int arr = 0; arr < 4; ++arr)
-                    dev_tma_load_2d(col_ring + (size_t)(st * 4 + arr) * MM_COL_TILE_BYTES, maps[arr], kb * MM_KB, (int)(J * MM_N),
-                                    &col_full[st]);
+                dev_mbar_arrive_expect_tx(&col_full[st], (unsigned)kStageBytes);
+                for (int arr = 0; arr < 4; ++arr) {
+                    if (!RESIDENT)
+                        for (int half = 0; half < MM_M / MM_N; ++half)
+                            dev_tma_load_2d(row_tile(st, arr, kb) + (size_t)half * MM_COL_TILE_BYTES, maps[arr], kb * MM_KB,
+                                            (int)(t0 + half * MM_N), &col_full[st]);
+                    dev_tma_load_2d(col_tile(st, arr), maps[arr], kb * MM_KB, (int)(J * MM_N), &col_full[st]);
+                }
             }
         }
         __syncwarp();
@@ -254,7 +272,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
         // (a lane that only polled a barrier its warp-mate acts on could miss a phase: the elected lane's commit lets
         //  the producer refill the stage, and two completions later the parity looks unfinished again)
         if (lane == 0) {
-            bool alive = dev_mbar_wait(&row_full, 0, a.status);
+            bool alive = RESIDENT ? dev_mbar_wait(&row_full, 0, a.status) : true;
             for (long long J = 0; alive && J < nJ; ++J) {
                 const int ab = (int)(J & 1);
                 const long long useA = J >> 1;
@@ -266,14 +284,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
                     const int st = (int)(q % MM_RING);
                     if (!dev_mbar_wait(&col_full[st], (unsigned)((q / MM_RING) & 1), a.status)) { alive = false; break; }   // K block landed
                     dev_tc_fence_after();
-                    const unsigned r_xh = dev_smem_u32(row_tiles + (size_t)(0 * nkb + kb) * MM_ROW_TILE_BYTES);
-                    const unsigned r_xl = dev_smem_u32(row_tiles + (size_t)(1 * nkb + kb) * MM_ROW_TILE_BYTES);
-                    const unsigned r_sh = dev_smem_u32(row_tiles + (size_t)(2 * nkb + kb) * MM_ROW_TILE_BYTES);
-                    const unsigned r_sl = dev_smem_u32(row_tiles + (size_t)(3 * nkb + kb) * MM_ROW_TILE_BYTES);
-                    const unsigned c_xh = dev_smem_u32(col_ring + (size_t)(st * 4 + 0) * MM_COL_TILE_BYTES);
-                    const unsigned c_xl = dev_smem_u32(col_ring + (size_t)(st * 4 + 1) * MM_COL_TILE_BYTES);
-                    const unsigned c_sh = dev_smem_u32(col_ring + (size_t)(st * 4 + 2) * MM_COL_TILE_BYTES);
-                    const unsigned c_sl = dev_smem_u32(col_ring + (size_t)(st * 4 + 3) * MM_COL_TILE_BYTES);
+                    const unsigned r_xh = dev_smem_u32(row_tile(st, 0, kb)), r_xl = dev_smem_u32(row_tile(st, 1, kb));
+                    const unsigned r_sh = dev_smem_u32(row_tile(st, 2, kb)), r_sl = dev_smem_u32(row_tile(st, 3, kb));
+                    const unsigned c_xh = dev_smem_u32(col_tile(st, 0)), c_xl = dev_smem_u32(col_tile(st, 1));
+                    const unsigned c_sh = dev_smem_u32(col_tile(st, 2)), c_sl = dev_smem_u32(col_tile(st, 3));
 #pragma unroll
                     for (int ks = 0; ks < MM_KB / 8; ++ks) {
                         const unsigned off = (unsigned)ks * 32u;                   // 8 tf32 = 32 bytes along K
@@ -356,8 +370,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) ksd_mma_kernel(KsdMmaArgs a, co
     if (warp == 1) dev_tmem_free512(tmem_base);
 }
 
+constexpr int MM_RESIDENT_MAX_KB = 2;                // row operands resident up to d = 64
 static inline size_t ksd_mma_smem_bytes(int nkb) {
-    return 1024 + (size_t)4 * nkb * MM_ROW_TILE_BYTES + (size_t)MM_RING * 4 * MM_COL_TILE_BYTES;
+    if (nkb <= MM_RESIDENT_MAX_KB) return 1024 + (size_t)4 * nkb * MM_ROW_TILE_BYTES + (size_t)MM_RING * 4 * MM_COL_TILE_BYTES;
+    return 1024 + (size_t)MM_RING * 4 * (MM_ROW_TILE_BYTES + MM_COL_TILE_BYTES);
 }
 
 }  // namespace gfk

@@ -6,11 +6,19 @@
 //
 // Data in HBM (caller owned): the standardised replica x, s (n x d row-major), optional
 // log-weights lw (n), and this rank's slice of the running objective A (rows x 1, float64).
-// One launch per greedy step: every thread first reduces the <= 16 (value, index) candidates
-// of the previous exchange to the selected row y, then streams its candidate rows once
-// (algorithmic traffic 16d + 16 (+8) bytes per row in float64), adds 2 k(x_i, y) to A_i and
-// keeps a running (min, first index).  Warp shuffle -> block -> last-block-done grid reduction
-// produces the rank's candidate for the next exchange.  No host round trip inside the loop.
+//
+// Kernels in this file:
+//   thin_persistent_kernel          d <= 4: ALL m greedy steps of a job in one cooperative launch; A, the log-weights
+//                                   and as many rows as fit stay on chip; per-step flag-in-data grid exchange
+//   thin_persistent_batched_kernel  the same loop for several independent chains, one group of CTAs per chain
+//   thin_step_small / chunked / tiled / tma kernels
+//                                   one launch per greedy step: every thread first reduces the <= 16 (value, index)
+//                                   candidates of the previous exchange to the selected row y, then streams its
+//                                   candidate rows once (16d + 16 (+8) bytes per row in float64), adds 2 k(x_i, y) to
+//                                   A_i and keeps a running (min, first index); warp shuffle -> block ->
+//                                   last-block-done grid reduction produces the rank's candidate for the next exchange
+// plus the cross-rank exchange (NCCL all-gather between launches, or peer mailboxes inside the kernels) and its
+// failure protocol.  No host round trip inside the greedy loop of either strategy.
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
