@@ -388,7 +388,8 @@ class SteinProblem:
 
 def thin_batched(problems, n_points):
     """``[p.thin(n_points) for p in problems]`` in ONE cooperative launch (``gfk_thin_batched``: one group of CTAs per
-    chain), for independent single-rank problems on one device.  Returns ``None`` - nothing launched - when the set is
+    chain), for independent problems on one device.  The launch is local to this rank whatever communicator is active
+    (chains are dealt over ranks by the caller, no exchange).  Returns ``None`` - nothing launched - when the set is
     not eligible (d > 4, mixed kernel kinds or precisions, a dense preconditioner, a chain too long for its CTA
     group); the caller then thins the chains one after the other."""
     lib = _lib.load()
@@ -399,7 +400,7 @@ def thin_batched(problems, n_points):
     if n == 0:
         return []
     device = problems[0].device
-    if any(p.device != device for p in problems) or lib.gfk_comm_size() != 1:
+    if any(p.device != device for p in problems):
         return None
     with torch.cuda.device(device):
         structs = (Problem * n)(*[p.struct for p in problems])

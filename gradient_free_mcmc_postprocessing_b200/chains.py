@@ -37,8 +37,15 @@ def _my_chains(n_chains, rank, world):
 
 def _thin_set(problems, n_points):
     """Index vectors of the problems: one batched launch when eligible, otherwise one job after the other."""
-    out = thin_batched(problems, n_points) if len(problems) > 1 else None
+    from . import _lib
+    local_only = _lib.load().gfk_comm_size() > 1     # a multi-rank communicator is active: SteinProblem.thin would shard
+    out = thin_batched(problems, n_points) if (len(problems) > 1 or local_only) else None
     if out is None:
+        if local_only and problems:
+            raise NotImplementedError(
+                'these chains are not eligible for the rank-local batched kernel (d > 4, a dense preconditioner or a '
+                'chain too long for shared memory) and a multi-rank communicator is active, under which thin() shards '
+                'ONE chain over all ranks: thin such chains with thin() / thin_gf(), or finalize the communicator first')
         out = [p.thin(n_points) for p in problems]
     return out
 

@@ -61,6 +61,17 @@ def main():
         dist.barrier()
     for k in ('GFK_PERSISTENT', 'GFK_P2P'):
         os.environ.pop(k, None)
+    # independent chains are dealt over the ranks and thinned by the rank-local batched launch - no exchange, although a
+    # multi-rank communicator is active (thin() itself would shard ONE chain over all ranks)
+    from gradient_free_mcmc_postprocessing_b200.chains import thin_chains
+    cs = [(x[i * 300:i * 300 + 900], g[i * 300:i * 300 + 900]) for i in range(5)]
+    got = thin_chains([c[0] for c in cs], [c[1] for c in cs], 12, preconditioner='med', rank=rank, world=world)
+    for i, c in enumerate(cs):
+        if i % world == rank:
+            assert np.array_equal(got[i], ot.thin(c[0], c[1], 12, preconditioner='med')), (rank, i)
+        else:
+            assert got[i] is None
+    dist.barrier()
     m = 400
     integ = _make_stein_gf_integrand(x[:m], log_p[:m], log_q[:m], g[:m], preconditioner='med')
     ref = ot._make_stein_gf_integrand(x[:m], log_p[:m], log_q[:m], g[:m], preconditioner='med')
