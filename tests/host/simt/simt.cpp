@@ -813,22 +813,49 @@ cudaError_t cudaFree(void* p) {
     if (!simt::in_arena(p)) free(p);   // arena blocks are never reused (test processes are short-lived)
     return cudaSuccess;
 }
-cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { memcpy(dst, src, bytes); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) {
+// Asynchronous device-to-host copies keep their real contract: the host buffer holds the data only after the stream has
+// been synchronised.  The value is snapshotted at enqueue time (everything enqueued earlier has run - the emulator
+// executes launches synchronously), the destination is poisoned, and the next synchronising call delivers it; host
+// code that reads the result of cudaMemcpyAsync without synchronising sees 0xA5 bytes instead of passing by accident.
+namespace simt {
+struct PendingD2H { void* dst; std::vector<unsigned char> data; };
+static std::mutex g_d2h_mu;
+static std::vector<PendingD2H> g_d2h;
+static void flush_d2h() {
+    std::lock_guard<std::mutex> lk(g_d2h_mu);
+    for (PendingD2H& c : g_d2h) memcpy(c.dst, c.data.data(), c.data.size());
+    g_d2h.clear();
+}
+}  // namespace simt
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) {
+    simt::flush_d2h();
+    memcpy(dst, src, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t) {
+    if (kind == cudaMemcpyDeviceToHost && bytes > 0) {
+        simt::PendingD2H c;
+        c.dst = dst;
+        c.data.assign(static_cast<const unsigned char*>(src), static_cast<const unsigned char*>(src) + bytes);
+        memset(dst, 0xa5, bytes);
+        std::lock_guard<std::mutex> lk(simt::g_d2h_mu);
+        simt::g_d2h.push_back(std::move(c));
+        return cudaSuccess;
+    }
     memcpy(dst, src, bytes);
     return cudaSuccess;
 }
 cudaError_t cudaMemset(void* p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return simt::g_last_error.load(); }
-cudaError_t cudaDeviceSynchronize() { return simt::g_last_error.load(); }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { simt::flush_d2h(); return simt::g_last_error.load(); }
+cudaError_t cudaDeviceSynchronize() { simt::flush_d2h(); return simt::g_last_error.load(); }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new SimtEvent{0.0}; return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
     e->t_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     return cudaSuccess;
 }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { simt::flush_d2h(); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
     if (!simt::in_arena(p)) return cudaErrorInvalidValue;
