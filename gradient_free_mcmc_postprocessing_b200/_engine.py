@@ -336,7 +336,7 @@ class SteinProblem:
             diag = torch.empty(m, dtype=torch.float64, device=self.device)
             ks = torch.empty(m, dtype=torch.float64, device=self.device)
             # opt-in (GFK_KSD_MMA=1): the row sums on the tensor cores - float32 mode, scalar preconditioner,
-            # 32 <= d <= 512 (csrc/ksd_mma.cuh; not yet measured on a GPU, hence not the default)
+            # d <= 512 (csrc/ksd_mma.cuh; not yet measured on a GPU, hence not the default)
             use_mma = (os.environ.get('GFK_KSD_MMA') == '1' and lib.gfk_ksd_mma_supported(ctypes.byref(self.struct)))
             if use_mma:
                 ws = _bytes(lib.gfk_ksd_mma_ws_bytes(m, self.d) + 256, self.device)

@@ -452,12 +452,12 @@ extern "C" int gfk_ksd_rowsums(const gfk_problem* p, const uint32_t* sel, int64_
     return rowsums_typed<double>(p, sel, m, part, n_parts, low, diag, st);
 }
 
-// ---- tensor-core row sums (ksd_mma.cuh): float32 mode, scalar preconditioner, 32 <= d <= 64 ----------------------
+// ---- tensor-core row sums (ksd_mma.cuh): float32 mode, scalar preconditioner, d <= 512 (padded to 32s) -------------
 static inline long long mma_pad_rows(long long m) { return (m + MM_M - 1) / MM_M * MM_M; }
 static inline int mma_pad_dims(int d) { return (d + MM_KB - 1) / MM_KB * MM_KB; }
 
 extern "C" int gfk_ksd_mma_supported(const gfk_problem* p) {
-    return (p && p->mode == GFK_F32_FAST && !p->xl && p->d >= 32 && p->d <= 512) ? 1 : 0;
+    return (p && p->mode == GFK_F32_FAST && !p->xl && p->d >= 1 && p->d <= 512) ? 1 : 0;
 }
 
 extern "C" size_t gfk_ksd_mma_ws_bytes(int64_t m, int32_t d) {
@@ -475,7 +475,7 @@ extern "C" int gfk_ksd_rowsums_mma(const gfk_problem* p, const uint32_t* sel, in
     GFK_REQUIRE(m < 0x7fffff00LL, "gfk_ksd_rowsums_mma: m too large for 32-bit tensor-map coordinates");
     GFK_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "gfk_ksd_rowsums_mma: bad part %d of %d", part, n_parts);
     if (!gfk_ksd_mma_supported(p)) {
-        set_error("gfk_ksd_rowsums_mma: needs the float32 mode, a scalar preconditioner and 32 <= d <= 512");
+        set_error("gfk_ksd_rowsums_mma: needs the float32 mode, a scalar preconditioner and d <= 512");
         return GFK_EUNSUPPORTED;
     }
     GFK_REQUIRE(reinterpret_cast<uintptr_t>(ws) % 256 == 0, "gfk_ksd_rowsums_mma: ws must be 256-byte aligned");

@@ -8,7 +8,7 @@
 //     <s_i, s_j>
 // i.e. four tile GEMMs  G1 = X X',  G2 = X S',  G3 = S X',  G4 = S S'  plus per-row scalars; everything after the dot
 // products (powers of the quadratic form, weights, triangular mask, row sums) is the epilogue of ksd_rowsum_kernel.
-// This is the float32 mode of the path (1e-5 relative on KSD values, BASELINE.json), for 32 <= d <= 512:
+// This is the float32 mode of the path (1e-5 relative on KSD values, BASELINE.json), for d <= 512:
 //
 //   * operands: tcgen05.mma kind::tf32 keeps 11 significant bits of an operand, far short of 1e-5, so every value
 //     is split v = hi + lo (hi = tf32(v), lo = tf32(v - hi): 22 bits together) by a prep kernel and a product is

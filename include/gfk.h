@@ -229,7 +229,7 @@ int gfk_ksd_finish(const double* low, const double* diag, int64_t m, double* ks,
  * large d the cross terms are GEMM-shaped": the four Gram tiles X X', X S', S X', S S' (report/report.tex:853-868) by
  * tcgen05.mma kind::tf32 with 3xTF32 operand splits (22 significant bits), operands fed by TMA, accumulators in
  * tensor memory, the pair epilogue of the tile kernel on top.  float32 mode only (1e-5 relative on KSD values), scalar
- * preconditioner, 32 <= d <= 512 (row operands resident in shared memory up to d = 64, streamed beyond): gfk_ksd_mma_supported(p) != 0; otherwise GFK_EUNSUPPORTED and nothing is launched.
+ * preconditioner, d <= 512 (row operands resident in shared memory up to d = 64, streamed beyond): gfk_ksd_mma_supported(p) != 0; otherwise GFK_EUNSUPPORTED and nothing is launched.
  * ws: gfk_ksd_mma_ws_bytes(m, d) bytes of device scratch, 256-byte aligned.  Asynchronous.
  * [round 2: executed on the CPU emulator of the test suite only, not yet on a GPU; opt-in from Python, GFK_KSD_MMA=1] */
 int gfk_ksd_mma_supported(const gfk_problem* p);

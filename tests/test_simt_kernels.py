@@ -697,7 +697,7 @@ def test_batched_chains_in_one_launch_equal_one_job_per_chain(sms, monkeypatch):
     assert np.array_equal(one[0][0], ot.thin(x4, g4, 5))
 
 
-@pytest.mark.parametrize('d', [32, 40, 64, 72, 130])
+@pytest.mark.parametrize('d', [1, 4, 10, 32, 40, 64, 72, 130])
 def test_tensor_core_ksd_row_sums(d):
     """gfk_ksd_rowsums_mma (csrc/ksd_mma.cuh): the four Gram tiles of the KSD on tcgen05.mma kind::tf32 with 3xTF32
     operand splits, operands by TMA into SWIZZLE_128B tiles, accumulators in tensor memory, the tile kernel's pair
@@ -739,10 +739,11 @@ def test_tensor_core_ksd_row_sums(d):
         sel = rng.integers(0, n, 200)
         lo_s, dg_s = p.ksd_rowsums_mma(sel=sel)
         np.testing.assert_allclose(p.ksd_from_rowsums(lo_s, dg_s), os_.ksd(lambda i, j: ref(sel[i], sel[j]), 200), rtol=1e-5)
-    # not eligible: float64 modes, d outside [32, 512]
+    # not eligible: float64 modes, a dense preconditioner
     assert H.SimProblem(x, g, preconditioner='med', precision='f64-fast').ksd_rowsums_mma() is None
-    xs, gs = _mcmc_like(rng, 100, 16)
-    assert H.SimProblem(xs, gs, preconditioner='med', precision='f32').ksd_rowsums_mma() is None
+    if d > 1:                                                # a 1 x 1 matrix is a scalar preconditioner
+        a = rng.standard_normal((d, d))
+        assert H.SimProblem(x, g, preconditioner=a @ a.T / d + np.eye(d), precision='f32').ksd_rowsums_mma() is None
 
 
 def test_a_lost_bulk_copy_ends_in_an_error_not_in_a_hang(monkeypatch):
