@@ -135,3 +135,77 @@ def test_kde_and_energy_match_scipy(seed, n, m, d, weighted, sms):
             assert abs(e2[t] - want) <= 1e-11 * max(1.0, abs(want))
     finally:
         os.environ.pop('SIMT_SMS', None)
+
+
+@settings(max_examples=int(os.environ.get('GFK_FUZZ_EXAMPLES', '25')), derandomize='GFK_FUZZ_EXAMPLES' not in os.environ,
+          deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(2, 420), d=st.integers(1, 80), m=st.integers(1, 300),
+       gf=st.booleans(), use_sel=st.booleans(), n_parts=st.integers(1, 3), offset=st.sampled_from([0.0, 2.0, 30.0]))
+def test_tensor_core_ksd_matches_oracle(seed, n, d, m, gf, use_sel, n_parts, offset):
+    """gfk_ksd_rowsums_mma (tcgen05.mma kind::tf32 with 3xTF32 splits, emulated) for arbitrary small problems: any d up to
+    80 (one to three K blocks, resident and streamed row operands), ragged tile edges, selections with repeats, the
+    128-row tiles dealt over 1-3 parts - cumulative KSD within the float32 bar of the float64 oracle."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)) + offset
+    g = -(x - offset) * (1.0 + 0.1 * np.arange(d)) / np.sqrt(d)
+    log_p = -0.5 * np.sum((x - offset) ** 2, axis=1) / d
+    log_q = log_p + 0.3 * np.sin(x[:, 0])
+    H.set_schedule(False)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        if gf:
+            ref = ot._make_stein_gf_integrand(x, log_p, log_q, g, preconditioner='med')
+            p = H.SimProblem(x, g, log_p, log_q, preconditioner='med', precision='f32')
+        else:
+            ref = ot._make_stein_integrand(x, g, preconditioner='med')
+            p = H.SimProblem(x, g, preconditioner='med', precision='f32')
+    if use_sel:
+        sel = rng.integers(0, n, m)
+        want = os_.ksd(lambda a, b: ref(sel[a], sel[b]), m)
+    else:
+        sel, m = None, n
+        want = os_.ksd(ref, n)
+    low, diag = np.zeros(m), np.zeros(m)
+    for part in range(n_parts):
+        lo, dg = p.ksd_rowsums_mma(sel=sel, m=m, part=part, n_parts=n_parts)
+        low += lo
+        diag += dg
+    np.testing.assert_allclose(p.ksd_from_rowsums(low, diag), want, rtol=1e-5)
+
+
+@settings(max_examples=int(os.environ.get('GFK_FUZZ_EXAMPLES', '15')), derandomize='GFK_FUZZ_EXAMPLES' not in os.environ,
+          deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 31 - 1), n_chains=st.integers(1, 5), d=st.integers(1, 4), m=st.integers(1, 20),
+       gf=st.booleans(), fast=st.booleans(), sms=st.integers(5, 14), dup=st.sampled_from([0.0, 0.5]))
+def test_batched_chains_match_oracle(seed, n_chains, d, m, gf, fast, sms, dup):
+    """gfk_thin_batched for arbitrary small sets of chains of different lengths: every chain's index vector and running
+    objective equal, bit for bit, what one gfk_thin per chain returns (which test_thinning_matches_oracle ties to the
+    oracle)."""
+    rng = np.random.default_rng(seed)
+    os.environ['SIMT_SMS'] = str(sms)
+    H.set_schedule(False)
+    try:
+        probs, chains = [], []
+        for _ in range(n_chains):
+            n = int(rng.integers(2, 1500))
+            base = rng.standard_normal((n, d)) + rng.standard_normal(d)
+            keep = rng.random(n) > dup
+            keep[0] = True
+            x = np.ascontiguousarray(base[np.maximum.accumulate(np.where(keep, np.arange(n), 0))])
+            if len(np.unique(x, axis=0)) < 2 or np.any(np.mean(np.abs(x - x.mean(0)), axis=0) == 0):
+                return
+            g = np.ascontiguousarray(-(x - x.mean(0)) * (1.0 + 0.2 * np.arange(d)))
+            log_p = -0.5 * np.sum((x - x.mean(0)) ** 2, axis=1)
+            log_q = log_p + 0.5 * np.sin(x[:, 0])
+            chains.append((x, g, log_p, log_q))
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                precision = 'f64-fast' if fast else 'f64'
+                probs.append(H.SimProblem(x, g, log_p, log_q, precision=precision) if gf else H.SimProblem(x, g, precision=precision))
+        got = H.thin_batched(probs, m)
+        assert got is not None
+        for c, p in enumerate(probs):
+            idx, obj = p.thin(m)
+            assert np.array_equal(got[0][c], idx) and np.array_equal(got[1][c], obj), c
+    finally:
+        os.environ.pop('SIMT_SMS', None)
