@@ -18,7 +18,7 @@ pids=()
 for f in api comm prep thin ksd proxy energy ${GFK_SIM_EXTRA_UNITS:-}; do
     [ -f "${csrc}/${f}.cu" ] || continue
     python "${here}/simt/cu2cpp.py" "${csrc}/${f}.cu" "${gen}/${f}.cpp"
-    g++ -std=c++17 -O2 -g -ffp-contract=off -fPIC -DGFK_SIMT_HOST=1 -Wno-unknown-pragmas -Wno-attributes ${GFK_SIM_CXXFLAGS:-} \
+    g++ -std=c++17 -O2 -g -ffp-contract=off -fPIC -DGFK_SIMT_HOST=1 -Wno-unknown-pragmas -Wno-attributes -Wno-psabi ${GFK_SIM_CXXFLAGS:-} \
         -I"${here}/simt/include" -I"${csrc}" -c "${gen}/${f}.cpp" -o "${gen}/${f}.o" &
     pids+=($!)
 done
