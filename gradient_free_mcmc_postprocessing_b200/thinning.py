@@ -45,6 +45,15 @@ def _greedy_search(n_points, integrand):
 
 
 def thin(sample, gradient, n_points, standardize=True, preconditioner='id', *, precision=None, device=None):
+    """Stein thinning: ``n_points`` greedily selected row indices (``np.ndarray[uint32]``, with replacement), exactly
+    ``stein_thinning.thinning.thin``.
+
+    Limits relative to the library the reference imports (neither is ever exercised by the reference, which fixes
+    c = 1, beta = -1/2 and uses scalar preconditioners, report/report.tex:435): the IMQ exponent is fixed at
+    beta = -1/2 (``kernel.vfk0_imq`` raises ``NotImplementedError`` for any other value); a dense preconditioner
+    (``'smpcov'``) must be symmetric and runs in the ``'f64-fast'`` formulation even when ``precision='f64'`` is asked
+    for (a ``UserWarning`` says so) - the strict, index-exact parity mode covers ``'id'``, ``'med'``, ``'sclmed'`` and
+    numeric-string preconditioners."""
     integrand = _make_stein_integrand(sample, gradient, standardize, preconditioner, precision=precision,
                                       device=device)
     return _greedy_search(n_points, integrand)
@@ -52,6 +61,9 @@ def thin(sample, gradient, n_points, standardize=True, preconditioner='id', *, p
 
 def thin_gf(sample, log_p, log_q, gradient_q, n_points, standardize=True, preconditioner='id', range_cap=None,
             *, precision=None, device=None):
+    """Gradient-free Stein thinning with proxy ``q`` (``stein_thinning.thinning.thin_gf``): the kernel is
+    ``exp(lw_i + lw_j) k_Q(x_i, x_j)`` with ``lw = log_q - log_p``; warns like the reference when the spread of ``lw``
+    exceeds 10.  Same limits as ``thin`` (beta = -1/2; dense preconditioners symmetric and in the FMA formulation)."""
     integrand = _make_stein_gf_integrand(sample, log_p, log_q, gradient_q, standardize, preconditioner,
                                          range_cap, precision=precision, device=device)
     return _greedy_search(n_points, integrand)
